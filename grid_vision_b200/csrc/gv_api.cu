@@ -1,0 +1,1327 @@
+// gv_api.cu — host side of the C ABI declared in include/gridvision_b200.h.
+//
+// Owns device memory, streams and (optionally) an NCCL communicator; every compute step is
+// a kernel from gv_kernels.cuh.  There is deliberately no CPU implementation of any step
+// here: if no sm_100 device is usable gv_create fails and nothing else can be called.
+#include "gridvision_b200.h"
+#include "gv_kernels.cuh"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#ifdef GV_WITH_NCCL
+#include <nccl.h>
+#endif
+
+using namespace gv;
+
+namespace {
+
+struct Scratch {
+  void *p = nullptr;
+  size_t cap = 0;
+};
+
+enum {
+  S_X, S_Y, S_Z, S_AOS, S_LAB, S_PIX, S_UV, S_BOX_RAW, S_BOX_F4, S_FRAME_OFF, S_BOX_OFF,
+  S_TILE_PREFIX, S_TILE_START, S_TILE_END, S_TILE_BOX, S_CELL, S_FLAGS, S_FOOT_IN, S_FOOT_LAB,
+  S_RECT, S_SMALL, S_OX, S_OY, S_OZ, S_SCAN0, S_SCAN1, S_SCAN2, S_SCAN3, S_UVZ, S_INDICES,
+  S_LABELS_IN, S_COUNT
+};
+
+constexpr size_t kPlanePad = 4096;  // slack cells so multi-GPU slabs can be equal-sized
+
+}  // namespace
+
+struct gv_ctx {
+  int device = 0;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+  std::vector<cudaEvent_t> events;
+  std::string err;
+
+  int ncam = 0;
+  CamDev cam[kMaxCam];
+
+  bool has_grid = false;
+  GridGeom g{};
+  size_t ncells = 0;
+  float *d_lo = nullptr, *d_occ = nullptr;
+  int32_t *d_hit = nullptr, *d_miss = nullptr;
+  unsigned long long *d_ends = nullptr;
+  uint2 *d_list = nullptr;
+  unsigned *d_list_count = nullptr;
+  bool counts_dirty = false, ends_dirty = false;
+
+  bool has_base = false;
+  float Tb[16];
+  BinDev bin{};
+
+  unsigned long long *d_stats = nullptr;  // beams, logical, physical, lines
+  unsigned long long launches = 0;
+  unsigned long long beams_bound = 0;  // host-side upper bound of beams since last finalize
+
+  Scratch s[S_COUNT];
+
+#ifdef GV_WITH_NCCL
+  ncclComm_t comm = nullptr;
+#endif
+  int rank = 0, world = 1;
+
+  int fail(int code, const char *fmt, ...)
+  {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    err = buf;
+    return code;
+  }
+};
+
+#define GV_CUDA(call)                                                                         \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return ctx->fail(GV_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),   \
+                       __FILE__, __LINE__);                                                   \
+  } while (0)
+
+#define GV_LAUNCH_CHECK()                                                                     \
+  do {                                                                                        \
+    ctx->launches++;                                                                          \
+    GV_CUDA(cudaPeekAtLastError());                                                           \
+  } while (0)
+
+#define GV_TRY(expr)                                                                          \
+  do {                                                                                        \
+    int rc_ = (expr);                                                                         \
+    if (rc_ != GV_OK) return rc_;                                                             \
+  } while (0)
+
+#define GV_REQUIRE(cond, code, ...)                                                           \
+  do {                                                                                        \
+    if (!(cond)) return ctx->fail(code, __VA_ARGS__);                                         \
+  } while (0)
+
+namespace {
+
+int reserve(gv_ctx *ctx, int slot, size_t bytes, void **out)
+{
+  Scratch &s = ctx->s[slot];
+  if (bytes == 0) bytes = 16;
+  if (s.cap < bytes) {
+    // growing a scratch slot may free memory a previous async kernel still reads
+    GV_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (s.p) GV_CUDA(cudaFree(s.p));
+    s.p = nullptr;
+    s.cap = 0;
+    size_t want = bytes + bytes / 8;
+    GV_CUDA(cudaMalloc(&s.p, want));
+    s.cap = want;
+  }
+  *out = s.p;
+  return GV_OK;
+}
+
+template <typename T>
+int reserve_t(gv_ctx *ctx, int slot, size_t count, T **out)
+{
+  void *p = nullptr;
+  GV_TRY(reserve(ctx, slot, count * sizeof(T), &p));
+  *out = static_cast<T *>(p);
+  return GV_OK;
+}
+
+cudaEvent_t get_event(gv_ctx *ctx, size_t i)
+{
+  while (ctx->events.size() <= i) {
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    ctx->events.push_back(e);
+  }
+  return ctx->events[i];
+}
+
+inline unsigned blocks_for(unsigned long long n, unsigned per_block)
+{
+  return (unsigned)((n + per_block - 1) / per_block);
+}
+
+bool float_exact(double v) { return (double)(float)v == v; }
+
+bool is_canonical_K(const double *K)
+{
+  return K[1] == 0.0 && K[3] == 0.0 && K[6] == 0.0 && K[7] == 0.0 && K[8] == 1.0 &&
+         float_exact(K[0]) && float_exact(K[2]) && float_exact(K[4]) && float_exact(K[5]);
+}
+
+void copy_T12(float dst[12], const float *T16)
+{
+  for (int i = 0; i < 12; ++i) dst[i] = T16[i];
+}
+
+// exclusive scan of n unsigned values in place (recursive CTA scan)
+int scan_u32(gv_ctx *ctx, unsigned *d, unsigned long long n, int level)
+{
+  if (n == 0) return GV_OK;
+  const unsigned nb = blocks_for(n, 1024);
+  unsigned *sums = nullptr;
+  if (nb > 1) GV_TRY(reserve_t(ctx, S_SCAN1 + level, (size_t)nb, &sums));
+  k_scan_block<<<nb, 1024, 0, ctx->stream>>>(d, n, sums);
+  GV_LAUNCH_CHECK();
+  if (nb > 1) {
+    GV_REQUIRE(level < 2, GV_ERR_INVALID, "scan_u32: input too large");
+    GV_TRY(scan_u32(ctx, sums, nb, level + 1));
+    k_scan_add<<<nb, 1024, 0, ctx->stream>>>(d, n, sums);
+    GV_LAUNCH_CHECK();
+  }
+  return GV_OK;
+}
+
+int upload_boxes(gv_ctx *ctx, const gv_box *boxes, int nboxes, bool on_device, float4 **out)
+{
+  static_assert(sizeof(gv_box) == 40 && sizeof(BoxRaw) == 40, "BoundingBox layout");
+  float4 *d_f4 = nullptr;
+  GV_TRY(reserve_t(ctx, S_BOX_F4, (size_t)(nboxes > 0 ? nboxes : 1), &d_f4));
+  if (nboxes > 0) {
+    const BoxRaw *d_raw = reinterpret_cast<const BoxRaw *>(boxes);
+    if (!on_device) {
+      BoxRaw *tmp = nullptr;
+      GV_TRY(reserve_t(ctx, S_BOX_RAW, (size_t)nboxes, &tmp));
+      GV_CUDA(cudaMemcpyAsync(tmp, boxes, (size_t)nboxes * sizeof(BoxRaw), cudaMemcpyHostToDevice,
+                              ctx->stream));
+      d_raw = tmp;
+    }
+    k_round_boxes<<<blocks_for(nboxes, 256), 256, 0, ctx->stream>>>(d_raw, nboxes, d_f4);
+    GV_LAUNCH_CHECK();
+  }
+  *out = d_f4;
+  return GV_OK;
+}
+
+int set_bin_params(gv_ctx *ctx, const gv_accum_params *prm, BinDev *out)
+{
+  GV_REQUIRE(ctx->has_grid, GV_ERR_STATE, "grid not initialised");
+  GV_REQUIRE(ctx->has_base, GV_ERR_STATE, "gv_set_base_transform not called");
+  GV_REQUIRE(prm != nullptr, GV_ERR_INVALID, "accum params are NULL");
+  GV_REQUIRE(prm->occ_mode == GV_OCC_ALL || prm->occ_mode == GV_OCC_LABELLED, GV_ERR_INVALID,
+             "bad occ_mode %d", prm->occ_mode);
+  *out = ctx->bin;
+  out->occ_mode = prm->occ_mode;
+  out->use_z_gate = prm->use_z_gate ? 1 : 0;
+  out->z_min = prm->z_min;
+  out->z_max = prm->z_max;
+  out->cap = prm->r_max > 0.0 ? 1 : 0;
+  out->r_max = prm->r_max;
+  out->rmax2 = prm->r_max * prm->r_max;
+  return GV_OK;
+}
+
+int note_beams(gv_ctx *ctx, unsigned long long n)
+{
+  const unsigned long long limit = 2147483647ull / (unsigned long long)ctx->world;
+  GV_REQUIRE(ctx->beams_bound + n <= limit, GV_ERR_OVERFLOW,
+             "more than %llu beams since the last finalize (int32 count planes)", limit);
+  ctx->beams_bound += n;
+  return GV_OK;
+}
+
+// K1/K2 launch for a single cloud (nframes == 0) in device memory
+int launch_points(gv_ctx *ctx, bool fuse, bool bin, PointArgs &a, unsigned ntiles, size_t smem)
+{
+  if (ntiles == 0) return GV_OK;
+  if (fuse && bin) k_points<true, true><<<ntiles, kThreads, smem, ctx->stream>>>(a);
+  else if (fuse) k_points<true, false><<<ntiles, kThreads, smem, ctx->stream>>>(a);
+  else k_points<false, true><<<ntiles, kThreads, smem, ctx->stream>>>(a);
+  GV_LAUNCH_CHECK();
+  return GV_OK;
+}
+
+void fill_point_args_cloud(gv_ctx *ctx, PointArgs &a, const float *x, const float *y,
+                           const float *z, size_t n, int is_dense)
+{
+  memset(&a, 0, sizeof(a));
+  a.x = x;
+  a.y = y;
+  a.z = z;
+  a.n = n;
+  a.is_dense = is_dense;
+  a.vec_ok = (((uintptr_t)x | (uintptr_t)y | (uintptr_t)z) & 15u) == 0;
+  a.stat_beams = ctx->d_stats;
+}
+
+int fuse_dev_impl(gv_ctx *ctx, const float *d_x, const float *d_y, const float *d_z, size_t n,
+                  int is_dense, const gv_box *boxes, int nboxes, bool boxes_on_device,
+                  const int32_t *box_cam_offsets, int16_t *d_labels, int32_t *d_pix, float *d_uv)
+{
+  GV_REQUIRE(ctx->ncam > 0, GV_ERR_STATE, "gv_set_cameras not called");
+  GV_REQUIRE(nboxes >= 0 && nboxes <= 32767, GV_ERR_INVALID, "nboxes %d out of range", nboxes);
+  GV_REQUIRE(nboxes == 0 || boxes != nullptr, GV_ERR_INVALID, "boxes is NULL");
+  GV_REQUIRE(ctx->ncam == 1 || box_cam_offsets != nullptr, GV_ERR_INVALID,
+             "box_cam_offsets required for %d cameras", ctx->ncam);
+  PointArgs a;
+  fill_point_args_cloud(ctx, a, d_x, d_y, d_z, n, is_dense);
+  a.ncam = ctx->ncam;
+  for (int c = 0; c < ctx->ncam; ++c) {
+    a.cam[c] = ctx->cam[c];
+    a.cam[c].box_begin = box_cam_offsets ? box_cam_offsets[c] : 0;
+    a.cam[c].box_end = box_cam_offsets ? box_cam_offsets[c + 1] : nboxes;
+    GV_REQUIRE(a.cam[c].box_begin >= 0 && a.cam[c].box_begin <= a.cam[c].box_end &&
+                 a.cam[c].box_end <= nboxes,
+               GV_ERR_INVALID, "box_cam_offsets[%d..%d] invalid", c, c + 1);
+  }
+  float4 *d_f4 = nullptr;
+  GV_TRY(upload_boxes(ctx, boxes, nboxes, boxes_on_device, &d_f4));
+  a.boxes = d_f4;
+  a.labels = d_labels;
+  a.pix = d_pix;
+  a.uv = d_uv;
+  const size_t smem = (size_t)(nboxes > 0 ? nboxes : 1) * sizeof(float4);
+  if (smem > 48 * 1024)
+    GV_CUDA(cudaFuncSetAttribute(k_points<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+  return launch_points(ctx, true, false, a, blocks_for(n, kTilePts), smem);
+}
+
+int accumulate_dev_impl(gv_ctx *ctx, const float *d_x, const float *d_y, const float *d_z, size_t n,
+                        const int16_t *d_labels, const gv_accum_params *prm, int32_t *d_cell,
+                        uint8_t *d_flags)
+{
+  PointArgs a;
+  fill_point_args_cloud(ctx, a, d_x, d_y, d_z, n, 0);
+  GV_TRY(set_bin_params(ctx, prm, &a.bin));
+  GV_REQUIRE(prm->occ_mode != GV_OCC_LABELLED || d_labels != nullptr, GV_ERR_INVALID,
+             "GV_OCC_LABELLED needs labels");
+  GV_TRY(note_beams(ctx, n));
+  a.labels_in = d_labels;
+  a.ends = ctx->d_ends;
+  a.cell_out = d_cell;
+  a.flags_out = d_flags;
+  ctx->ends_dirty = true;
+  return launch_points(ctx, false, true, a, blocks_for(n, kTilePts), 16);
+}
+
+int raycast_flush_impl(gv_ctx *ctx, unsigned rank, unsigned world)
+{
+  if (!ctx->ends_dirty) return GV_OK;
+  GV_CUDA(cudaMemsetAsync(ctx->d_list_count, 0, sizeof(unsigned), ctx->stream));
+  const unsigned nb = (unsigned)ctx->num_sms * 8u;
+  k_ends_compact<<<nb, kThreads, 0, ctx->stream>>>(ctx->d_ends, ctx->ncells, ctx->d_hit,
+                                                   ctx->d_miss, ctx->d_list, ctx->d_list_count,
+                                                   rank, world);
+  GV_LAUNCH_CHECK();
+  k_raycast_lines<<<nb, kThreads, 0, ctx->stream>>>(ctx->d_list, ctx->d_list_count, ctx->bin.sx,
+                                                    ctx->bin.sy, ctx->g.nx, ctx->d_miss,
+                                                    ctx->d_stats + 1);
+  GV_LAUNCH_CHECK();
+  ctx->ends_dirty = false;
+  ctx->counts_dirty = true;
+  return GV_OK;
+}
+
+// footprints -> device rect list.  mode 0 corners (n x 8), 1 poses (n x 4), 2 points (n x 2 + labels)
+int footprint_rects(gv_ctx *ctx, const double *in, const int32_t *labels, int n, int mode,
+                    int4 **d_rects_out)
+{
+  *d_rects_out = nullptr;
+  if (n <= 0) return GV_OK;
+  GV_REQUIRE(in != nullptr, GV_ERR_INVALID, "footprint array is NULL");
+  const int per = mode == 0 ? 8 : (mode == 1 ? 4 : 2);
+  double *d_in = nullptr;
+  int32_t *d_lab = nullptr;
+  int4 *d_rect = nullptr;
+  GV_TRY(reserve_t(ctx, S_FOOT_IN, (size_t)n * per, &d_in));
+  GV_TRY(reserve_t(ctx, S_RECT, (size_t)n, &d_rect));
+  GV_CUDA(cudaMemcpyAsync(d_in, in, (size_t)n * per * sizeof(double), cudaMemcpyHostToDevice,
+                          ctx->stream));
+  if (mode == 2) {
+    GV_REQUIRE(labels != nullptr, GV_ERR_INVALID, "labels is NULL");
+    GV_TRY(reserve_t(ctx, S_FOOT_LAB, (size_t)n, &d_lab));
+    GV_CUDA(cudaMemcpyAsync(d_lab, labels, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice,
+                            ctx->stream));
+  }
+  k_footprint_rects<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(d_in, d_lab, n, mode, ctx->g, d_rect);
+  GV_LAUNCH_CHECK();
+  *d_rects_out = d_rect;
+  return GV_OK;
+}
+
+int finalize_slab(gv_ctx *ctx, int32_t k_decay, const int4 *d_rects, int nfoot, size_t cell0,
+                  size_t ncell, bool counts)
+{
+  if (ncell == 0) return GV_OK;
+  FinalizeArgs fa;
+  fa.log_odds = ctx->d_lo;
+  fa.occupancy = ctx->d_occ;
+  fa.hit = ctx->d_hit;
+  fa.miss = ctx->d_miss;
+  fa.cell0 = cell0;
+  fa.ncell = ncell;
+  fa.nx = ctx->g.nx;
+  fa.decay = (float)k_decay * -0.2f;  // log_odds_decay_, ref: occupancy_grid.hpp:29
+  fa.rects = d_rects;
+  fa.nfoot = d_rects ? nfoot : 0;
+  const unsigned nb = blocks_for(ncell, kThreads * 4);
+  if (counts) k_finalize<true><<<nb, kThreads, 0, ctx->stream>>>(fa);
+  else k_finalize<false><<<nb, kThreads, 0, ctx->stream>>>(fa);
+  GV_LAUNCH_CHECK();
+  return GV_OK;
+}
+
+int finalize_impl(gv_ctx *ctx, int32_t k_decay, const double *in, const int32_t *labels, int n,
+                  int mode)
+{
+  GV_REQUIRE(ctx->has_grid, GV_ERR_STATE, "grid not initialised");
+  GV_REQUIRE(n >= 0, GV_ERR_INVALID, "negative footprint count");
+  GV_TRY(raycast_flush_impl(ctx, 0, 1));
+  int4 *d_rects = nullptr;
+  GV_TRY(footprint_rects(ctx, in, labels, n, mode, &d_rects));
+  GV_TRY(finalize_slab(ctx, k_decay, d_rects, n, 0, ctx->ncells, ctx->counts_dirty));
+  ctx->counts_dirty = false;
+  ctx->beams_bound = 0;
+  return GV_OK;
+}
+
+void free_grid(gv_ctx *ctx)
+{
+  cudaFree(ctx->d_lo);
+  cudaFree(ctx->d_occ);
+  cudaFree(ctx->d_hit);
+  cudaFree(ctx->d_miss);
+  cudaFree(ctx->d_ends);
+  cudaFree(ctx->d_list);
+  ctx->d_lo = ctx->d_occ = nullptr;
+  ctx->d_hit = ctx->d_miss = nullptr;
+  ctx->d_ends = nullptr;
+  ctx->d_list = nullptr;
+  ctx->has_grid = false;
+}
+
+int refresh_origin(gv_ctx *ctx)
+{
+  // start cell + continuous index coordinates of the sensor origin, computed by the same
+  // device getIndex every beam uses
+  if (!(ctx->has_grid && ctx->has_base)) return GV_OK;
+  OriginOut *d_o = nullptr;
+  GV_TRY(reserve_t(ctx, S_SMALL, 1, &d_o));
+  const double ox = (double)ctx->Tb[3], oy = (double)ctx->Tb[7];
+  k_origin_setup<<<1, 1, 0, ctx->stream>>>(ox, oy, ctx->g, d_o);
+  GV_LAUNCH_CHECK();
+  OriginOut o;
+  GV_CUDA(cudaMemcpyAsync(&o, d_o, sizeof(o), cudaMemcpyDeviceToHost, ctx->stream));
+  GV_CUDA(cudaStreamSynchronize(ctx->stream));
+  BinDev &b = ctx->bin;
+  copy_T12(b.T, ctx->Tb);
+  b.g = ctx->g;
+  b.ox = ox;
+  b.oy = oy;
+  b.oax = o.oax;
+  b.oay = o.oay;
+  b.sx = o.sx;
+  b.sy = o.sy;
+  b.origin_ok = o.ok;
+  return GV_OK;
+}
+
+int grid_init_impl(gv_ctx *ctx, double length_x, double length_y, double res, double pos_x,
+                   double pos_y)
+{
+  GV_REQUIRE(res > 0.0 && length_x > 0.0 && length_y > 0.0, GV_ERR_INVALID,
+             "grid geometry must be positive");
+  // grid_map::GridMap::setGeometry: size = (int)round(length/resolution); length = size*res
+  const double sx = std::round(length_x / res), sy = std::round(length_y / res);
+  GV_REQUIRE(sx >= 1.0 && sy >= 1.0 && sx * sy <= 2147483647.0, GV_ERR_INVALID,
+             "grid of %.0f x %.0f cells unsupported", sx, sy);
+  GV_CUDA(cudaStreamSynchronize(ctx->stream));
+  free_grid(ctx);
+  GridGeom &g = ctx->g;
+  g.nx = (int)sx;
+  g.ny = (int)sy;
+  g.res = res;
+  g.len_x = (double)g.nx * res;
+  g.len_y = (double)g.ny * res;
+  g.pos_x = pos_x;
+  g.pos_y = pos_y;
+  g.half_x = 0.5 * g.len_x;
+  g.half_y = 0.5 * g.len_y;
+  ctx->ncells = (size_t)g.nx * (size_t)g.ny;
+  const size_t padded = ctx->ncells + kPlanePad;
+  GV_CUDA(cudaMalloc(&ctx->d_lo, padded * sizeof(float)));
+  GV_CUDA(cudaMalloc(&ctx->d_occ, padded * sizeof(float)));
+  GV_CUDA(cudaMalloc(&ctx->d_hit, padded * sizeof(int32_t)));
+  GV_CUDA(cudaMalloc(&ctx->d_miss, padded * sizeof(int32_t)));
+  GV_CUDA(cudaMalloc(&ctx->d_ends, padded * sizeof(unsigned long long)));
+  GV_CUDA(cudaMalloc(&ctx->d_list, ctx->ncells * sizeof(uint2)));
+  ctx->has_grid = true;
+  GV_CUDA(cudaMemsetAsync(ctx->d_lo, 0, padded * sizeof(float), ctx->stream));
+  GV_CUDA(cudaMemsetAsync(ctx->d_occ, 0, padded * sizeof(float), ctx->stream));
+  GV_CUDA(cudaMemsetAsync(ctx->d_hit, 0, padded * sizeof(int32_t), ctx->stream));
+  GV_CUDA(cudaMemsetAsync(ctx->d_miss, 0, padded * sizeof(int32_t), ctx->stream));
+  GV_CUDA(cudaMemsetAsync(ctx->d_ends, 0, padded * sizeof(unsigned long long), ctx->stream));
+  // ref: src/occupancy_grid.cpp:12-13 log_odds = log_odds_prior_ (0.0f), occupancy = 0.5f
+  k_fill_f32<<<ctx->num_sms * 4, kThreads, 0, ctx->stream>>>(ctx->d_occ, ctx->ncells, 0.5f);
+  GV_LAUNCH_CHECK();
+  ctx->counts_dirty = ctx->ends_dirty = false;
+  ctx->beams_bound = 0;
+  GV_CUDA(cudaMemsetAsync(ctx->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
+  return refresh_origin(ctx);
+}
+
+}  // namespace
+
+// =====================================================================================
+// lifecycle
+// =====================================================================================
+extern "C" {
+
+int gv_version(void) { return GV_VERSION; }
+
+const char *gv_status_string(int status)
+{
+  switch (status) {
+  case GV_OK: return "ok";
+  case GV_ERR_INVALID: return "invalid argument";
+  case GV_ERR_CUDA: return "CUDA error";
+  case GV_ERR_STATE: return "invalid call order";
+  case GV_ERR_NCCL: return "NCCL error";
+  case GV_ERR_OVERFLOW: return "count overflow";
+  case GV_ERR_NO_DEVICE: return "no usable sm_100 device";
+  default: return "unknown status";
+  }
+}
+
+int gv_create(gv_ctx **out, int device)
+{
+  if (!out) return GV_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+    cudaGetLastError();
+    return GV_ERR_NO_DEVICE;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return GV_ERR_NO_DEVICE;
+  // the library carries sm_100a SASS only: refuse anything else instead of failing at launch
+  if (prop.major != 10) return GV_ERR_NO_DEVICE;
+  gv_ctx *ctx = new (std::nothrow) gv_ctx();
+  if (!ctx) return GV_ERR_INVALID;
+  ctx->device = device;
+  ctx->num_sms = prop.multiProcessorCount;
+  if (cudaSetDevice(device) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMalloc(&ctx->d_stats, 4 * sizeof(unsigned long long)) != cudaSuccess ||
+      cudaMalloc(&ctx->d_list_count, sizeof(unsigned)) != cudaSuccess ||
+      cudaMemset(ctx->d_stats, 0, 4 * sizeof(unsigned long long)) != cudaSuccess) {
+    cudaGetLastError();
+    gv_destroy(ctx);
+    return GV_ERR_CUDA;
+  }
+  ctx->stream = ctx->own_stream;
+  *out = ctx;
+  return GV_OK;
+}
+
+void gv_destroy(gv_ctx *ctx)
+{
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+#ifdef GV_WITH_NCCL
+  if (ctx->comm) ncclCommDestroy(ctx->comm);
+#endif
+  free_grid(ctx);
+  for (auto &s : ctx->s) cudaFree(s.p);
+  cudaFree(ctx->d_stats);
+  cudaFree(ctx->d_list_count);
+  for (auto e : ctx->events) cudaEventDestroy(e);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
+  if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
+  cudaGetLastError();
+  delete ctx;
+}
+
+const char *gv_last_error(const gv_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int gv_synchronize(gv_ctx *ctx)
+{
+  if (!ctx) return GV_ERR_INVALID;
+  GV_CUDA(cudaSetDevice(ctx->device));
+  GV_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GV_OK;
+}
+
+void *gv_stream(gv_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int gv_set_stream(gv_ctx *ctx, void *stream)
+{
+  if (!ctx) return GV_ERR_INVALID;
+  GV_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->stream = stream ? (cudaStream_t)stream : ctx->own_stream;
+  return GV_OK;
+}
+
+int gv_get_stats(gv_ctx *ctx, gv_stats *out)
+{
+  if (!ctx || !out) return GV_ERR_INVALID;
+  unsigned long long h[4];
+  GV_CUDA(cudaMemcpyAsync(h, ctx->d_stats, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  GV_CUDA(cudaStreamSynchronize(ctx->stream));
+  out->beams = h[0];
+  out->cells_logical = h[1];
+  out->cells_physical = h[2];
+  out->distinct_ends = h[3];
+  out->kernel_launches = ctx->launches;
+  return GV_OK;
+}
+
+// =====================================================================================
+// fusion
+// =====================================================================================
+int gv_set_cameras(gv_ctx *ctx, int ncam, const double *K, const float *T_cam_lidar,
+                   const int32_t *wh)
+{
+  if (!ctx) return GV_ERR_INVALID;
+  GV_REQUIRE(ncam >= 1 && ncam <= kMaxCam, GV_ERR_INVALID, "ncam %d not in [1,%d]", ncam, kMaxCam);
+  GV_REQUIRE(K && wh, GV_ERR_INVALID, "K / wh is NULL");
+  for (int c = 0; c < ncam; ++c) {
+    GV_REQUIRE(wh[2 * c] > 0 && wh[2 * c + 1] > 0, GV_ERR_INVALID, "camera %d image size", c);
+    CamDev &d = ctx->cam[c];
+    memset(&d, 0, sizeof(d));
+    for (int i = 0; i < 9; ++i) d.K[i] = K[9 * c + i];
+    d.has_T = T_cam_lidar != nullptr;
+    if (d.has_T) copy_T12(d.T, T_cam_lidar + 16 * c);
+    d.W = wh[2 * c];
+    d.H = wh[2 * c + 1];
+    d.Wf = (float)d.W;
+    d.Hf = (float)d.H;
+    d.canon = is_canonical_K(d.K) ? 1 : 0;
+  }
+  ctx->ncam = ncam;
+  return GV_OK;
+}
+
+int gv_fuse_dev(gv_ctx *ctx, const float *d_x, const float *d_y, const float *d_z, size_t n,
+                int is_dense, const gv_box *d_boxes, int nboxes, const int32_t *box_cam_offsets,
+                int16_t *d_labels_out, int32_t *d_pix_out, float *d_uv_out)
+{
+  if (!ctx) return GV_ERR_INVALID;
+  GV_CUDA(cudaSetDevice(ctx->device));
+  GV_REQUIRE(n == 0 || (d_x && d_y && d_z), GV_ERR_INVALID, "point planes are NULL");
+  return fuse_dev_impl(ctx, d_x, d_y, d_z, n, is_dense, d_boxes, nboxes, true, box_cam_offsets,
+                       d_labels_out, d_pix_out, d_uv_out);
+}
+
+static int fuse_host_impl(gv_ctx *ctx, const float *d_x, const float *d_y, const float *d_z,
+                          size_t n, int is_dense, const gv_box *boxes, int nboxes,
+                          const int32_t *box_cam_offsets, int16_t *labels_out, int32_t *pix_out,
+                          float *uv_out)
+{
+  const size_t planes = (size_t)ctx->ncam * n;
+  int16_t *d_lab = nullptr;
+  int32_t *d_pix = nullptr;
+  float *d_uv = nullptr;
+  if (labels_out) GV_TRY(reserve_t(ctx, S_LAB, planes, &d_lab));
+  if (pix_out) GV_TRY(reserve_t(ctx, S_PIX, planes, &d_pix));
+  if (uv_out) GV_TRY(reserve_t(ctx, S_UV, 2 * planes, &d_uv));
+  GV_TRY(fuse_dev_impl(ctx, d_x, d_y, d_z, n, is_dense, boxes, nboxes, false, box_cam_offsets,
+                       d_lab, d_pix, d_uv));
+  if (labels_out)
+    GV_CUDA(cudaMemcpyAsync(labels_out, d_lab, planes * sizeof(int16_t), cudaMemcpyDeviceToHost,
+                            ctx->stream));
+  if (pix_out)
+    GV_CUDA(cudaMemcpyAsync(pix_out, d_pix, planes * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                            ctx->stream));
+  if (uv_out)
+    GV_CUDA(cudaMemcpyAsync(uv_out, d_uv, 2 * planes * sizeof(float), cudaMemcpyDeviceToHost,
+                            ctx->stream));
+  GV_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GV_OK;
+}
+
+static int upload_cloud(gv_ctx *ctx, const float *x, const float *y, const float *z, size_t n,
+                        float **d_x, float **d_y, float **d_z)
+{
+  GV_REQUIRE(n == 0 || (x && y && z), GV_ERR_INVALID, "point planes are NULL");
+  GV_TRY(reserve_t(ctx, S_X, n, d_x));
+  GV_TRY(reserve_t(ctx, S_Y, n, d_y));
+  GV_TRY(reserve_t(ctx, S_Z, n, d_z));
+  if (n) {
+    GV_CUDA(cudaMemcpyAsync(*d_x, x, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    GV_CUDA(cudaMemcpyAsync(*d_y, y, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    GV_CUDA(cudaMemcpyAsync(*d_z, z, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  return GV_OK;
+}
+
+int gv_fuse(gv_ctx *ctx, const float *x, const float *y, const float *z, size_t n, int is_dense,
+            const gv_box *boxes, int nboxes, const int32_t *box_cam_offsets, int16_t *labels_out,
+            int32_t *pix_out, float *uv_out)
+{
+  if (!ctx) return GV_ERR_INVALID;
+  GV_CUDA(cudaSetDevice(ctx->device));
+  GV_REQUIRE(ctx->ncam > 0, GV_ERR_STATE, "gv_set_cameras not called");
+  float *d_x, *d_y, *d_z;
+  GV_TRY(upload_cloud(ctx, x, y, z, n, &d_x, &d_y, &d_z));
+  return fuse_host_impl(ctx, d_x, d_y, d_z, n, is_dense, boxes, nboxes, box_cam_offsets,
+                        labels_out, pix_out, uv_out);
+}
+
+int gv_fuse_aos32(gv_ctx *ctx, const gv_point_xyzi *pts, size_t n, int is_dense,
+                  const gv_box *boxes, int nboxes, const int32_t *box_cam_offsets,
+                  int16_t *labels_out, int32_t *pix_out, float *uv_out)
+{
+  if (!ctx) return GV_ERR_INVALID;
+  GV_CUDA(cudaSetDevice(ctx->device));
+  GV_REQUIRE(ctx->ncam > 0, GV_ERR_STATE, "gv_set_cameras not called");
+  GV_REQUIRE(n == 0 || pts, GV_ERR_INVALID, "pts is NULL");
+  static_assert(sizeof(gv_point_xyzi) == 32, "pcl::PointXYZI layout");
+  float4 *d_aos = nullptr;
+  float *d_x, *d_y, *d_z;
+  GV_TRY(reserve_t(ctx, S_AOS, 2 * n, &d_aos));
+  GV_TRY(reserve_t(ctx, S_X, n, &d_x));
+  GV_TRY(reserve_t(ctx, S_Y, n, &d_y));
+  GV_TRY(reserve_t(ctx, S_Z, n, &d_z));
+  if (n) {
+    GV_CUDA(cudaMemcpyAsync(d_aos, pts, n * sizeof(gv_point_xyzi), cudaMemcpyHostToDevice,
+                            ctx->stream));
+    k_aos32_to_soa<<<blocks_for(n, kThreads), kThreads, 0, ctx->stream>>>(d_aos, n, d_x, d_y, d_z);
+    GV_LAUNCH_CHECK();
+  }
+  return fuse_host_impl(ctx, d_x, d_y, d_z, n, is_dense, boxes, nboxes, box_cam_offsets,
+                        labels_out, pix_out, uv_out);
+}
+
+int gv_transform_points(gv_ctx *ctx, int cam, const float *x, const float *y, const float *z,
+                        size_t n, int is_dense, float *ox, float *oy, float *oz)
+{
+  if (!ctx) return GV_ERR_INVALID;
+  GV_CUDA(cudaSetDevice(ctx->device));
+  GV_REQUIRE(cam >= 0 && cam < ctx->ncam, GV_ERR_STATE, "camera %d not set", cam);
+  GV_REQUIRE(ctx->cam[cam].has_T, GV_ERR_STATE, "camera %d has no extrinsic", cam);
+  GV_REQUIRE(n == 0 || (ox && oy && oz), GV_ERR_INVALID, "output planes are NULL");
+  float *d_x, *d_y, *d_z, *d_ox, *d_oy, *d_oz;
+  GV_TRY(upload_cloud(ctx, x, y, z, n, &d_x, &d_y, &d_z));
+  GV_TRY(reserve_t(ctx, S_OX, n, &d_ox));
+  GV_TRY(reserve_t(ctx, S_OY, n, &d_oy));
+  GV_TRY(reserve_t(ctx, S_OZ, n, &d_oz));
+  if (n) {
+    k_transform<<<blocks_for(n, kThreads), kThreads, 0, ctx->stream>>>(d_x, d_y, d_z, n, is_dense,
+                                                                      ctx->cam[cam], d_ox, d_oy,
+                                                                      d_oz);
+    GV_LAUNCH_CHECK();
+    GV_CUDA(cudaMemcpyAsync(ox, d_ox, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    GV_CUDA(cudaMemcpyAsync(oy, d_oy, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    GV_CUDA(cudaMemcpyAsync(oz, d_oz, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  GV_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GV_OK;
+}
+
+int gv_project_kdtree(gv_ctx *ctx, int cam, const float *x, const float *y, const float *z,
+                      size_t n, float *uvz_out, size_t *m_out)
+{
+  if (!ctx) return GV_ERR_INVALID;
+  GV_CUDA(cudaSetDevice(ctx->device));
+  GV_REQUIRE(cam >= 0 && cam < ctx->ncam, GV_ERR_STATE, "camera %d not set", cam);
+  GV_REQUIRE(m_out != nullptr, GV_ERR_INVALID, "m_out is NULL");
+  *m_out = 0;
+  if (n == 0) return GV_OK;
+  GV_REQUIRE(uvz_out != nullptr, GV_ERR_INVALID, "uvz_out is NULL");
+  float *d_x, *d_y, *d_z, *d_uvz;
+  unsigned *d_cnt;
+  GV_TRY(upload_cloud(ctx, x, y, z, n, &d_x, &d_y, &d_z));
+  const unsigned nb = blocks_for(n, kThreads);
+  GV_TRY(reserve_t(ctx, S_SCAN0, (size_t)nb + 1, &d_cnt));
+  GV_TRY(reserve_t(ctx, S_UVZ, 3 * n, &d_uvz));
+  GV_CUDA(cudaMemsetAsync(d_cnt + nb, 0, sizeof(unsigned), ctx->stream));
+  k_kdtree_count<<<nb, kThreads, 0, ctx->stream>>>(d_x, d_y, d_z, n, 0, ctx->cam[cam], d_cnt);
+  GV_LAUNCH_CHECK();
+  GV_TRY(scan_u32(ctx, d_cnt, (unsigned long long)nb + 1, 0));
+  k_kdtree_scatter<<<nb, kThreads, 0, ctx->stream>>>(d_x, d_y, d_z, n, 0, ctx->cam[cam], d_cnt,
+                                                     d_uvz);
+  GV_LAUNCH_CHECK();
+  unsigned total = 0;
+  GV_CUDA(cudaMemcpyAsync(&total, d_cnt + nb, sizeof(unsigned), cudaMemcpyDeviceToHost,
+                          ctx->stream));
+  GV_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (total)
+    GV_CUDA(cudaMemcpyAsync(uvz_out, d_uvz, (size_t)total * 3 * sizeof(float),
+                            cudaMemcpyDeviceToHost, ctx->stream));
+  GV_CUDA(cudaStreamSynchronize(ctx->stream));
+  *m_out = total;
+  return GV_OK;
+}
+
+int gv_partition_by_label(gv_ctx *ctx, const int16_t *labels, size_t n, int nboxes,
+                          uint32_t *indices_out, uint64_t *offsets_out)
+{
+  if (!ctx) return GV_ERR_INVALID;
+  GV_CUDA(cudaSetDevice(ctx->device));
+  GV_REQUIRE(nboxes >= 0 && nboxes <= 1024, GV_ERR_INVALID, "nboxes %d not in [0,1024]", nboxes);
+  GV_REQUIRE(offsets_out != nullptr, GV_ERR_INVALID, "offsets_out is NULL");
+  GV_REQUIRE(n < 4294967296ull, GV_ERR_INVALID, "n too large for 32-bit indices");
+  for (int b = 0; b <= nboxes; ++b) offsets_out[b] = 0;
+  if (n == 0 || nboxes == 0) return GV_OK;
+  GV_REQUIRE(labels && indices_out, GV_ERR_INVALID, "labels / indices_out is NULL");
+  const unsigned nb = blocks_for(n, kThreads);
+  const unsigned long long hn = (unsigned long long)nboxes * nb;
+  int16_t *d_lab;
+  unsigned *d_hist, *d_idx;
+  GV_TRY(reserve_t(ctx, S_LABELS_IN, n, &d_lab));
+  GV_TRY(reserve_t(ctx, S_SCAN0, (size_t)hn + 1, &d_hist));
+  GV_TRY(reserve_t(ctx, S_INDICES, n, &d_idx));
+  GV_CUDA(cudaMemcpyAsync(d_lab, labels, n * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
+  GV_CUDA(cudaMemsetAsync(d_hist + hn, 0, sizeof(unsigned), ctx->stream));
+  k_label_hist<<<nb, kThreads, (size_t)nboxes * sizeof(unsigned), ctx->stream>>>(d_lab, n, nboxes,
+                                                                                 nb, d_hist);
+  GV_LAUNCH_CHECK();
+  GV_TRY(scan_u32(ctx, d_hist, hn + 1, 0));
+  const size_t smem = (size_t)nboxes * (kThreads / 32) * sizeof(unsigned);
+  k_label_scatter<<<nb, kThreads, smem, ctx->stream>>>(d_lab, n, nboxes, nb, d_hist, d_idx);
+  GV_LAUNCH_CHECK();
+  // per-box offsets are the scanned histogram at block 0 of each label
+  std::vector<unsigned> h_off((size_t)nboxes + 1);
+  GV_CUDA(cudaMemcpy2DAsync(h_off.data(), sizeof(unsigned), d_hist, (size_t)nb * sizeof(unsigned),
+                            sizeof(unsigned), (size_t)nboxes, cudaMemcpyDeviceToHost, ctx->stream));
+  GV_CUDA(cudaMemcpyAsync(&h_off[nboxes], d_hist + hn, sizeof(unsigned), cudaMemcpyDeviceToHost,
+                          ctx->stream));
+  GV_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int b = 0; b <= nboxes; ++b) offsets_out[b] = h_off[b];
+  if (h_off[nboxes])
+    GV_CUDA(cudaMemcpyAsync(indices_out, d_idx, (size_t)h_off[nboxes] * sizeof(unsigned),
+                            cudaMemcpyDeviceToHost, ctx->stream));
+  GV_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GV_OK;
+}
+
+// =====================================================================================
+// grid state
+// =====================================================================================
+int gv_grid_init(gv_ctx *ctx, double length_x, double length_y, double resolution, double pos_x,
+                 double pos_y)
+{
+  if (!ctx) return GV_ERR_INVALID;
+  GV_CUDA(cudaSetDevice(ctx->device));
+  return grid_init_impl(ctx, length_x, length_y, resolution, pos_x, pos_y);
+}
+
+int gv_grid_init_reference(gv_ctx *ctx, uint8_t grid_x, uint8_t grid_y, double resolution)
+{
+  if (!ctx) return GV_ERR_INVALID;
+  GV_CUDA(cudaSetDevice(ctx->device));
+  // ref: src/occupancy_grid.cpp:10-11  Length(grid_x, grid_y), Position(grid_x / 3, 0.0):
+  // uint8_t / int -> integer division
+  return grid_init_impl(ctx, (double)grid_x, (double)grid_y, resolution, (double)(grid_x / 3), 0.0);
+}
+
+int gv_grid_get_desc(gv_ctx *ctx, gv_grid_desc *out)
+{
+  if (!ctx || !out) return GV_ERR_INVALID;
+  GV_REQUIRE(ctx->has_grid, GV_ERR_STATE, "grid not initialised");
+  out->nx = ctx->g.nx;
+  out->ny = ctx->g.ny;
+  out->resolution = ctx->g.res;
+  out->length_x = ctx->g.len_x;
+  out->length_y = ctx->g.len_y;
+  out->pos_x = ctx->g.pos_x;
+  out->pos_y = ctx->g.pos_y;
+  return GV_OK;
+}
+
+int gv_grid_reset(gv_ctx *ctx)
+{
+  if (!ctx) return GV_ERR_INVALID;
+  GV_CUDA(cudaSetDevice(ctx->device));
+  GV_REQUIRE(ctx->has_grid, GV_ERR_STATE, "grid not initialised");
+  const size_t padded = ctx->ncells + kPlanePad;
+  GV_CUDA(cudaMemsetAsync(ctx->d_lo, 0, padded * sizeof(float), ctx->stream));
+  GV_CUDA(cudaMemsetAsync(ctx->d_hit, 0, padded * sizeof(int32_t), ctx->stream));
+  GV_CUDA(cudaMemsetAsync(ctx->d_miss, 0, padded * sizeof(int32_t), ctx->stream));
+  GV_CUDA(cudaMemsetAsync(ctx->d_ends, 0, padded * sizeof(unsigned long long), ctx->stream));
+  k_fill_f32<<<ctx->num_sms * 4, kThreads, 0, ctx->stream>>>(ctx->d_occ, ctx->ncells, 0.5f);
+  GV_LAUNCH_CHECK();
+  GV_CUDA(cudaMemsetAsync(ctx->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
+  ctx->counts_dirty = ctx->ends_dirty = false;
+  ctx->beams_bound = 0;
+  return GV_OK;
+}
+
+int gv_grid_upload(gv_ctx *ctx, const float *log_odds, const float *occupancy)
+{
+  if (!ctx) return GV_ERR_INVALID;
+  GV_CUDA(cudaSetDevice(ctx->device));
+  GV_REQUIRE(ctx->has_grid, GV_ERR_STATE, "grid not initialised");
+  const size_t bytes = ctx->ncells * sizeof(float);
+  if (log_odds)
+    GV_CUDA(cudaMemcpyAsync(ctx->d_lo, log_odds, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  if (occupancy)
+    GV_CUDA(cudaMemcpyAsync(ctx->d_occ, occupancy, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  GV_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GV_OK;
+}
+
+int gv_grid_download(gv_ctx *ctx, float *log_odds, float *occupancy)
+{
+  if (!ctx) return GV_ERR_INVALID;
+  GV_CUDA(cudaSetDevice(ctx->device));
+  GV_REQUIRE(ctx->has_grid, GV_ERR_STATE, "grid not initialised");
+  const size_t bytes = ctx->ncells * sizeof(float);
+  if (log_odds)
+    GV_CUDA(cudaMemcpyAsync(log_odds, ctx->d_lo, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  if (occupancy)
+    GV_CUDA(cudaMemcpyAsync(occupancy, ctx->d_occ, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  GV_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GV_OK;
+}
+
+int gv_grid_counts_download(gv_ctx *ctx, int32_t *hit, int32_t *miss)
+{
+  if (!ctx) return GV_ERR_INVALID;
+  GV_CUDA(cudaSetDevice(ctx->device));
+  GV_REQUIRE(ctx->has_grid, GV_ERR_STATE, "grid not initialised");
+  GV_TRY(raycast_flush_impl(ctx, 0, 1));
+  const size_t bytes = ctx->ncells * sizeof(int32_t);
+  if (hit) GV_CUDA(cudaMemcpyAsync(hit, ctx->d_hit, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  if (miss) GV_CUDA(cudaMemcpyAsync(miss, ctx->d_miss, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  GV_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GV_OK;
+}
+
+int gv_grid_layers_dev(gv_ctx *ctx, float **d_log_odds, float **d_occupancy, int32_t **d_hit,
+                       int32_t **d_miss)
+{
+  if (!ctx) return GV_ERR_INVALID;
+  GV_REQUIRE(ctx->has_grid, GV_ERR_STATE, "grid not initialised");
+  if (d_log_odds) *d_log_odds = ctx->d_lo;
+  if (d_occupancy) *d_occupancy = ctx->d_occ;
+  if (d_hit) *d_hit = ctx->d_hit;
+  if (d_miss) *d_miss = ctx->d_miss;
+  return GV_OK;
+}
+
+int gv_grid_get_index(gv_ctx *ctx, const double *xy, int n, int32_t *ixy_out)
+{
+  if (!ctx) return GV_ERR_INVALID;
+  GV_CUDA(cudaSetDevice(ctx->device));
+  GV_REQUIRE(ctx->has_grid, GV_ERR_STATE, "grid not initialised");
+  if (n <= 0) return GV_OK;
+  GV_REQUIRE(xy && ixy_out, GV_ERR_INVALID, "xy / ixy_out is NULL");
+  double *d_in;
+  int32_t *d_out;
+  GV_TRY(reserve_t(ctx, S_FOOT_IN, (size_t)2 * n, &d_in));
+  GV_TRY(reserve_t(ctx, S_CELL, (size_t)2 * n, &d_out));
+  GV_CUDA(cudaMemcpyAsync(d_in, xy, (size_t)2 * n * sizeof(double), cudaMemcpyHostToDevice,
+                          ctx->stream));
+  k_get_index<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(d_in, n, ctx->g, d_out);
+  GV_LAUNCH_CHECK();
+  GV_CUDA(cudaMemcpyAsync(ixy_out, d_out, (size_t)2 * n * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                          ctx->stream));
+  GV_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GV_OK;
+}
+
+// =====================================================================================
+// per-frame updates R7 / R8 / R9
+// =====================================================================================
+int gv_grid_update(gv_ctx *ctx)
+{
+  if (!ctx) return GV_ERR_INVALID;
+  GV_CUDA(cudaSetDevice(ctx->device));
+  return finalize_impl(ctx, 1, nullptr, nullptr, 0, 0);
+}
+
+int gv_grid_update_poses(gv_ctx *ctx, const double *xylw, int n)
+{
+  if (!ctx) return GV_ERR_INVALID;
+  GV_CUDA(cudaSetDevice(ctx->device));
+  return finalize_impl(ctx, 1, xylw, nullptr, n, 1);
+}
+
+int gv_grid_update_points(gv_ctx *ctx, const double *xy, const int32_t *labels, int n)
+{
+  if (!ctx) return GV_ERR_INVALID;
+  GV_CUDA(cudaSetDevice(ctx->device));
+  return finalize_impl(ctx, 1, xy, labels, n, 2);
+}
+
+int gv_grid_update_corners(gv_ctx *ctx, const double *corners, int n)
+{
+  if (!ctx) return GV_ERR_INVALID;
+  GV_CUDA(cudaSetDevice(ctx->device));
+  return finalize_impl(ctx, 1, corners, nullptr, n, 0);
+}
+
+// =====================================================================================
+// binning + raycast + finalise
+// =====================================================================================
+int gv_set_base_transform(gv_ctx *ctx, const float *T_base_lidar)
+{
+  if (!ctx) return GV_ERR_INVALID;
+  GV_CUDA(cudaSetDevice(ctx->device));
+  GV_REQUIRE(T_base_lidar != nullptr, GV_ERR_INVALID, "T_base_lidar is NULL");
+  // beams binned under the previous pose belong to the previous start cell: walk them first
+  if (ctx->has_grid && ctx->ends_dirty) GV_TRY(raycast_flush_impl(ctx, 0, 1));
+  memcpy(ctx->Tb, T_base_lidar, sizeof(ctx->Tb));
+  ctx->has_base = true;
+  return refresh_origin(ctx);
+}
+
+int gv_grid_accumulate_dev(gv_ctx *ctx, const float *d_x, const float *d_y, const float *d_z,
+                           size_t n, const int16_t *d_labels, const gv_accum_params *prm,
+                           int32_t *d_cell_out, uint8_t *d_flags_out)
+{
+  if (!ctx) return GV_ERR_INVALID;
+  GV_CUDA(cudaSetDevice(ctx->device));
+  GV_REQUIRE(n == 0 || (d_x && d_y && d_z), GV_ERR_INVALID, "point planes are NULL");
+  return accumulate_dev_impl(ctx, d_x, d_y, d_z, n, d_labels, prm, d_cell_out, d_flags_out);
+}
+
+int gv_grid_accumulate(gv_ctx *ctx, const float *x, const float *y, const float *z, size_t n,
+                       const int16_t *labels, const gv_accum_params *prm, int32_t *cell_out,
+                       uint8_t *flags_out)
+{
+  if (!ctx) return GV_ERR_INVALID;
+  GV_CUDA(cudaSetDevice(ctx->device));
+  float *d_x, *d_y, *d_z;
+  GV_TRY(upload_cloud(ctx, x, y, z, n, &d_x, &d_y, &d_z));
+  int16_t *d_lab = nullptr;
+  int32_t *d_cell = nullptr;
+  uint8_t *d_flags = nullptr;
+  if (labels) {
+    GV_TRY(reserve_t(ctx, S_LABELS_IN, n, &d_lab));
+    GV_CUDA(cudaMemcpyAsync(d_lab, labels, n * sizeof(int16_t), cudaMemcpyHostToDevice,
+                            ctx->stream));
+  }
+  if (cell_out) GV_TRY(reserve_t(ctx, S_CELL, n, &d_cell));
+  if (flags_out) GV_TRY(reserve_t(ctx, S_FLAGS, n, &d_flags));
+  GV_TRY(accumulate_dev_impl(ctx, d_x, d_y, d_z, n, d_lab, prm, d_cell, d_flags));
+  if (cell_out && n)
+    GV_CUDA(cudaMemcpyAsync(cell_out, d_cell, n * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                            ctx->stream));
+  if (flags_out && n)
+    GV_CUDA(cudaMemcpyAsync(flags_out, d_flags, n * sizeof(uint8_t), cudaMemcpyDeviceToHost,
+                            ctx->stream));
+  GV_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GV_OK;
+}
+
+int gv_grid_raycast_flush(gv_ctx *ctx)
+{
+  if (!ctx) return GV_ERR_INVALID;
+  GV_CUDA(cudaSetDevice(ctx->device));
+  GV_REQUIRE(ctx->has_grid, GV_ERR_STATE, "grid not initialised");
+  return raycast_flush_impl(ctx, 0, 1);
+}
+
+int gv_grid_finalize(gv_ctx *ctx, int32_t k_decay, const double *corners, int nfoot)
+{
+  if (!ctx) return GV_ERR_INVALID;
+  GV_CUDA(cudaSetDevice(ctx->device));
+  return finalize_impl(ctx, k_decay, corners, nullptr, nfoot, 0);
+}
+
+// ---- batch: the whole hot path, one kernel pass over the points ------------------------
+static int process_batch_impl(gv_ctx *ctx, const float *px, const float *py, const float *pz,
+                              bool points_on_device, const uint64_t *frame_offsets, int nframes,
+                              const gv_box *boxes, bool boxes_on_device,
+                              const int32_t *box_frame_offsets, const gv_accum_params *prm,
+                              int16_t *labels_out)
+{
+  GV_REQUIRE(ctx->ncam >= 1, GV_ERR_STATE, "gv_set_cameras not called");
+  GV_REQUIRE(nframes >= 0, GV_ERR_INVALID, "negative frame count");
+  if (nframes == 0) return GV_OK;
+  GV_REQUIRE(frame_offsets && box_frame_offsets, GV_ERR_INVALID, "offset arrays are NULL");
+  const uint64_t p0 = frame_offsets[0];
+  const uint64_t n = frame_offsets[nframes] - p0;
+  const int nboxes = box_frame_offsets[nframes];
+  GV_REQUIRE(box_frame_offsets[0] == 0, GV_ERR_INVALID, "box_frame_offsets[0] must be 0");
+  GV_REQUIRE(nboxes == 0 || boxes, GV_ERR_INVALID, "boxes is NULL");
+  GV_REQUIRE(n == 0 || (px && py && pz), GV_ERR_INVALID, "point planes are NULL");
+
+  PointArgs a;
+  memset(&a, 0, sizeof(a));
+  GV_TRY(set_bin_params(ctx, prm, &a.bin));
+  GV_TRY(note_beams(ctx, n));
+
+  // tile table: one entry per 1024-point tile, tiles never straddle frames
+  std::vector<unsigned> tile_prefix((size_t)nframes + 1);
+  int max_boxes = 1;
+  unsigned long long ntiles64 = 0;
+  for (int f = 0; f < nframes; ++f) {
+    GV_REQUIRE(frame_offsets[f + 1] >= frame_offsets[f], GV_ERR_INVALID,
+               "frame_offsets not monotone at %d", f);
+    const int nb = box_frame_offsets[f + 1] - box_frame_offsets[f];
+    GV_REQUIRE(nb >= 0 && nb <= 32767, GV_ERR_INVALID, "frame %d has %d boxes", f, nb);
+    if (nb > max_boxes) max_boxes = nb;
+    tile_prefix[f] = (unsigned)ntiles64;
+    ntiles64 += (frame_offsets[f + 1] - frame_offsets[f] + kTilePts - 1) / kTilePts;
+    GV_REQUIRE(ntiles64 < 2147483647ull, GV_ERR_INVALID, "batch too large");
+  }
+  tile_prefix[nframes] = (unsigned)ntiles64;
+  const unsigned ntiles = (unsigned)ntiles64;
+
+  unsigned long long *d_foff, *d_tstart, *d_tend;
+  int *d_boff;
+  unsigned *d_tprefix;
+  int2 *d_tbox;
+  GV_TRY(reserve_t(ctx, S_FRAME_OFF, (size_t)nframes + 1, &d_foff));
+  GV_TRY(reserve_t(ctx, S_BOX_OFF, (size_t)nframes + 1, &d_boff));
+  GV_TRY(reserve_t(ctx, S_TILE_PREFIX, (size_t)nframes + 1, &d_tprefix));
+  GV_TRY(reserve_t(ctx, S_TILE_START, (size_t)ntiles, &d_tstart));
+  GV_TRY(reserve_t(ctx, S_TILE_END, (size_t)ntiles, &d_tend));
+  GV_TRY(reserve_t(ctx, S_TILE_BOX, (size_t)ntiles, &d_tbox));
+
+  // points: device-resident, or staged per chunk from host memory
+  const float *d_x = px, *d_y = py, *d_z = pz;
+  int16_t *d_lab = labels_out;
+  uint64_t base = 0;  // offset subtracted from frame offsets (host path rebases to 0)
+  if (!points_on_device) {
+    float *tx, *ty, *tz;
+    GV_TRY(reserve_t(ctx, S_X, n, &tx));
+    GV_TRY(reserve_t(ctx, S_Y, n, &ty));
+    GV_TRY(reserve_t(ctx, S_Z, n, &tz));
+    d_x = tx;
+    d_y = ty;
+    d_z = tz;
+    base = p0;
+    if (labels_out) GV_TRY(reserve_t(ctx, S_LAB, n, &d_lab));
+  }
+  std::vector<unsigned long long> foff((size_t)nframes + 1);
+  for (int f = 0; f <= nframes; ++f) foff[f] = frame_offsets[f] - base;
+
+  GV_CUDA(cudaMemcpyAsync(d_foff, foff.data(), foff.size() * sizeof(unsigned long long),
+                          cudaMemcpyHostToDevice, ctx->stream));
+  GV_CUDA(cudaMemcpyAsync(d_boff, box_frame_offsets, ((size_t)nframes + 1) * sizeof(int),
+                          cudaMemcpyHostToDevice, ctx->stream));
+  GV_CUDA(cudaMemcpyAsync(d_tprefix, tile_prefix.data(), tile_prefix.size() * sizeof(unsigned),
+                          cudaMemcpyHostToDevice, ctx->stream));
+  k_build_tiles<<<nframes, 128, 0, ctx->stream>>>(d_foff, d_boff, d_tprefix, nframes, d_tstart,
+                                                 d_tend, d_tbox);
+  GV_LAUNCH_CHECK();
+  float4 *d_f4 = nullptr;
+  GV_TRY(upload_boxes(ctx, boxes, nboxes, boxes_on_device, &d_f4));
+  // host staging below reads foff/tile_prefix only on the host; the async copies above read
+  // pageable host vectors, so make sure they are consumed before the vectors die
+  GV_CUDA(cudaStreamSynchronize(ctx->stream));
+
+  a.x = d_x;
+  a.y = d_y;
+  a.z = d_z;
+  a.n = points_on_device ? frame_offsets[nframes] : n;
+  a.is_dense = 0;
+  a.vec_ok = (((uintptr_t)d_x | (uintptr_t)d_y | (uintptr_t)d_z) & 15u) == 0;
+  a.ncam = 1;
+  a.cam[0] = ctx->cam[0];
+  a.boxes = d_f4;
+  a.labels = d_lab;
+  a.nframes = nframes;
+  a.tile_start = d_tstart;
+  a.tile_end = d_tend;
+  a.tile_boxes = d_tbox;
+  a.ends = ctx->d_ends;
+  a.stat_beams = ctx->d_stats;
+  ctx->ends_dirty = true;
+  const size_t smem = (size_t)max_boxes * sizeof(float4);
+  if (smem > 48 * 1024)
+    GV_CUDA(cudaFuncSetAttribute(k_points<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+
+  if (points_on_device) {
+    a.tile0 = 0;
+    return launch_points(ctx, true, true, a, ntiles, smem);
+  }
+
+  // host path: pipeline H2D copies, the fused kernel and the label D2H over three streams,
+  // a few frames per chunk (~4M points), so PCIe runs in both directions under the compute
+  const uint64_t chunk_pts = 4ull << 20;
+  size_t ev = 0;
+  int f0 = 0;
+  while (f0 < nframes) {
+    int f1 = f0 + 1;
+    while (f1 < nframes && foff[f1 + 1] - foff[f0] <= chunk_pts) ++f1;
+    const uint64_t c0 = foff[f0], c1 = foff[f1];
+    const size_t bytes = (size_t)(c1 - c0) * sizeof(float);
+    cudaEvent_t e_h2d = get_event(ctx, ev++), e_k = get_event(ctx, ev++);
+    GV_REQUIRE(e_h2d && e_k, GV_ERR_CUDA, "cudaEventCreate failed");
+    if (bytes) {
+      GV_CUDA(cudaMemcpyAsync((float *)d_x + c0, px + p0 + c0, bytes, cudaMemcpyHostToDevice,
+                              ctx->h2d_stream));
+      GV_CUDA(cudaMemcpyAsync((float *)d_y + c0, py + p0 + c0, bytes, cudaMemcpyHostToDevice,
+                              ctx->h2d_stream));
+      GV_CUDA(cudaMemcpyAsync((float *)d_z + c0, pz + p0 + c0, bytes, cudaMemcpyHostToDevice,
+                              ctx->h2d_stream));
+    }
+    GV_CUDA(cudaEventRecord(e_h2d, ctx->h2d_stream));
+    GV_CUDA(cudaStreamWaitEvent(ctx->stream, e_h2d, 0));
+    a.tile0 = tile_prefix[f0];
+    GV_TRY(launch_points(ctx, true, true, a, tile_prefix[f1] - tile_prefix[f0], smem));
+    if (labels_out && c1 > c0) {
+      GV_CUDA(cudaEventRecord(e_k, ctx->stream));
+      GV_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, e_k, 0));
+      GV_CUDA(cudaMemcpyAsync(labels_out + p0 + c0, d_lab + c0, (size_t)(c1 - c0) * sizeof(int16_t),
+                              cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    }
+    f0 = f1;
+  }
+  GV_CUDA(cudaStreamSynchronize(ctx->d2h_stream));
+  GV_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GV_OK;
+}
+
+int gv_process_batch(gv_ctx *ctx, const float *x, const float *y, const float *z,
+                     const uint64_t *frame_offsets, int nframes, const gv_box *boxes,
+                     const int32_t *box_frame_offsets, const gv_accum_params *prm,
+                     int16_t *labels_out)
+{
+  if (!ctx) return GV_ERR_INVALID;
+  GV_CUDA(cudaSetDevice(ctx->device));
+  return process_batch_impl(ctx, x, y, z, false, frame_offsets, nframes, boxes, false,
+                            box_frame_offsets, prm, labels_out);
+}
+
+int gv_process_batch_dev(gv_ctx *ctx, const float *d_x, const float *d_y, const float *d_z,
+                         const uint64_t *frame_offsets, int nframes, const gv_box *d_boxes,
+                         const int32_t *box_frame_offsets, const gv_accum_params *prm,
+                         int16_t *d_labels_out)
+{
+  if (!ctx) return GV_ERR_INVALID;
+  GV_CUDA(cudaSetDevice(ctx->device));
+  return process_batch_impl(ctx, d_x, d_y, d_z, true, frame_offsets, nframes, d_boxes, true,
+                            box_frame_offsets, prm, d_labels_out);
+}
+
+// =====================================================================================
+// consumers
+// =====================================================================================
+int gv_grid_to_occupancy(gv_ctx *ctx, int8_t *data_out)
+{
+  if (!ctx) return GV_ERR_INVALID;
+  GV_CUDA(cudaSetDevice(ctx->device));
+  GV_REQUIRE(ctx->has_grid, GV_ERR_STATE, "grid not initialised");
+  GV_REQUIRE(data_out != nullptr, GV_ERR_INVALID, "data_out is NULL");
+  int8_t *d_out;
+  GV_TRY(reserve_t(ctx, S_FLAGS, ctx->ncells, &d_out));
+  k_to_occupancy<<<blocks_for(ctx->ncells, kThreads), kThreads, 0, ctx->stream>>>(ctx->d_occ,
+                                                                                 ctx->ncells, d_out);
+  GV_LAUNCH_CHECK();
+  GV_CUDA(cudaMemcpyAsync(data_out, d_out, ctx->ncells, cudaMemcpyDeviceToHost, ctx->stream));
+  GV_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GV_OK;
+}
+
+// =====================================================================================
+// multi-GPU
+// =====================================================================================
+#ifdef GV_WITH_NCCL
+#define GV_NCCL(call)                                                                         \
+  do {                                                                                        \
+    ncclResult_t r_ = (call);                                                                 \
+    if (r_ != ncclSuccess)                                                                    \
+      return ctx->fail(GV_ERR_NCCL, "%s failed: %s", #call, ncclGetErrorString(r_));          \
+  } while (0)
+#endif
+
+int gv_nccl_unique_id(void *id128_out)
+{
+#ifdef GV_WITH_NCCL
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  if (!id128_out) return GV_ERR_INVALID;
+  ncclUniqueId id;
+  if (ncclGetUniqueId(&id) != ncclSuccess) return GV_ERR_NCCL;
+  memcpy(id128_out, &id, sizeof(id));
+  return GV_OK;
+#else
+  (void)id128_out;
+  return GV_ERR_NCCL;
+#endif
+}
+
+int gv_nccl_init(gv_ctx *ctx, const void *id128, int rank, int world)
+{
+  if (!ctx) return GV_ERR_INVALID;
+#ifdef GV_WITH_NCCL
+  GV_CUDA(cudaSetDevice(ctx->device));
+  GV_REQUIRE(id128 && world >= 1 && rank >= 0 && rank < world && world <= 64, GV_ERR_INVALID,
+             "bad rank/world %d/%d", rank, world);
+  GV_REQUIRE(ctx->comm == nullptr, GV_ERR_STATE, "communicator already initialised");
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  GV_NCCL(ncclCommInitRank(&ctx->comm, world, id, rank));
+  ctx->rank = rank;
+  ctx->world = world;
+  return GV_OK;
+#else
+  (void)id128; (void)rank; (void)world;
+  return ctx->fail(GV_ERR_NCCL, "library built without NCCL");
+#endif
+}
+
+int gv_nccl_world(gv_ctx *ctx, int *rank_out, int *world_out)
+{
+  if (!ctx) return GV_ERR_INVALID;
+  if (rank_out) *rank_out = ctx->rank;
+  if (world_out) *world_out = ctx->world;
+  return GV_OK;
+}
+
+int gv_grid_finalize_multi(gv_ctx *ctx, int32_t k_decay, const double *corners, int nfoot)
+{
+  if (!ctx) return GV_ERR_INVALID;
+  GV_CUDA(cudaSetDevice(ctx->device));
+  GV_REQUIRE(ctx->has_grid, GV_ERR_STATE, "grid not initialised");
+#ifdef GV_WITH_NCCL
+  if (ctx->world == 1 || ctx->comm == nullptr) return finalize_impl(ctx, k_decay, corners, nullptr, nfoot, 0);
+  const unsigned world = (unsigned)ctx->world, rank = (unsigned)ctx->rank;
+  // equal slabs, 4-cell aligned (k_finalize vector width); planes carry kPlanePad slack cells
+  size_t slab = (ctx->ncells + world - 1) / world;
+  slab = (slab + 3) & ~(size_t)3;
+  GV_REQUIRE(slab * world <= ctx->ncells + kPlanePad, GV_ERR_INVALID, "grid too small for %u ranks", world);
+  // 1. every rank learns every rank's binned beams: exact u64 sum of the (total,hit) plane
+  GV_NCCL(ncclAllReduce(ctx->d_ends, ctx->d_ends, ctx->ncells, ncclUint64, ncclSum, ctx->comm,
+                        ctx->stream));
+  // 2. the de-duplicated raycast is split by end cell (lin % world), partial planes result
+  ctx->ends_dirty = true;  // a rank with no local beams still owns a share of the lines
+  GV_TRY(raycast_flush_impl(ctx, rank, world));
+  // 3. exact int32 sums of the partial planes, scattered by slab
+  GV_NCCL(ncclGroupStart());
+  GV_NCCL(ncclReduceScatter(ctx->d_hit, ctx->d_hit + (size_t)rank * slab, slab, ncclInt32, ncclSum,
+                            ctx->comm, ctx->stream));
+  GV_NCCL(ncclReduceScatter(ctx->d_miss, ctx->d_miss + (size_t)rank * slab, slab, ncclInt32,
+                            ncclSum, ctx->comm, ctx->stream));
+  GV_NCCL(ncclGroupEnd());
+  // 4. finalise the local slab
+  int4 *d_rects = nullptr;
+  GV_TRY(footprint_rects(ctx, corners, nullptr, nfoot, 0, &d_rects));
+  const size_t c0 = (size_t)rank * slab;
+  const size_t c1 = c0 + slab < ctx->ncells ? c0 + slab : ctx->ncells;
+  if (c1 > c0) GV_TRY(finalize_slab(ctx, k_decay, d_rects, nfoot, c0, c1 - c0, true));
+  const size_t padded = ctx->ncells + kPlanePad;
+  GV_CUDA(cudaMemsetAsync(ctx->d_hit, 0, padded * sizeof(int32_t), ctx->stream));
+  GV_CUDA(cudaMemsetAsync(ctx->d_miss, 0, padded * sizeof(int32_t), ctx->stream));
+  // 5. every rank ends with the full grid
+  GV_NCCL(ncclGroupStart());
+  GV_NCCL(ncclAllGather(ctx->d_lo + c0, ctx->d_lo, slab, ncclFloat32, ctx->comm, ctx->stream));
+  GV_NCCL(ncclAllGather(ctx->d_occ + c0, ctx->d_occ, slab, ncclFloat32, ctx->comm, ctx->stream));
+  GV_NCCL(ncclGroupEnd());
+  ctx->counts_dirty = false;
+  ctx->beams_bound = 0;
+  return GV_OK;
+#else
+  if (ctx->world == 1) return finalize_impl(ctx, k_decay, corners, nullptr, nfoot, 0);
+  return ctx->fail(GV_ERR_NCCL, "library built without NCCL");
+#endif
+}
+
+}  // extern "C"

@@ -1,0 +1,969 @@
+// gv_kernels.cuh — sm_100a kernels for the grid-vision point-cloud -> occupancy-grid path.
+//
+// Every parity-critical floating-point operation is written with an explicit
+// round-to-nearest intrinsic (__fmul_rn, __dadd_rn, __ddiv_rn, ...) so nvcc can never
+// contract a multiply-add into an FMA: the reference CPU build has no FMA
+// (baseline x86-64, /root/reference CMakeLists.txt:1-8) and the summation order is part
+// of the contract.  __fma_rn is used only where both products are exact in double, so
+// that fma(a,b,c) == RN(a*b + c) by construction (see project_point).
+//
+// No tensor cores anywhere: nothing on this path is a dense contraction.  The kernels are
+// HBM-streaming (points, grid planes) or atomic-bound (binning, raycast).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gv {
+
+constexpr int kMaxCam = 8;
+constexpr int kThreads = 256;
+constexpr int kPtsPerThread = 4;
+constexpr int kTilePts = kThreads * kPtsPerThread;  // 1024 points per CTA tile
+constexpr int kMaxFootCand = 256;
+
+// ----------------------------------------------------------------------------------
+// parameter blocks (passed by value as __grid_constant__, no __constant__ state so that
+// several contexts/streams can share a device)
+// ----------------------------------------------------------------------------------
+struct CamDev {
+  double K[9];   // row-major intrinsics
+  float T[12];   // row-major 3x4 T_cam<-lidar
+  float Wf, Hf;  // (float)image_width/height: the reference compares float u against int W
+  int W, H;
+  int has_T;     // 0: cloud already in the camera frame
+  int canon;     // K == [fx 0 cx; 0 fy cy; 0 0 1] with float-representable entries
+  int box_begin, box_end;
+};
+
+struct GridGeom {
+  int nx, ny;
+  double res, len_x, len_y, pos_x, pos_y, half_x, half_y;  // half = 0.5*len (exact)
+};
+
+struct BinDev {
+  float T[12];  // row-major 3x4 T_base<-lidar
+  GridGeom g;
+  double ox, oy;    // sensor origin in the base frame (translation column, promoted)
+  double oax, oay;  // its continuous index coordinates
+  int sx, sy;       // origin cell
+  int origin_ok;
+  int occ_mode, use_z_gate;
+  float z_min, z_max;
+  double r_max, rmax2;
+  int cap;
+};
+
+struct PointArgs {
+  const float *x, *y, *z;
+  unsigned long long n;
+  int is_dense;
+  int vec_ok;  // x,y,z base pointers are 16-byte aligned
+  // fusion
+  int ncam;
+  CamDev cam[kMaxCam];
+  const float4 *boxes;  // (x_min, y_min, x_max, y_max) pre-rounded to float, see round_boxes
+  int16_t *labels;      // cam-major planes, stride n (nullable)
+  int32_t *pix;         // nullable
+  float *uv;            // nullable
+  // batch mode (per-frame box lists, camera 0 only); nframes == 0 -> single cloud
+  int nframes;
+  unsigned tile0;                        // first tile of this launch (chunked batches)
+  const unsigned long long *tile_start;  // [ntiles] first point of the tile
+  const unsigned long long *tile_end;    // [ntiles] end of the tile's frame (exclusive)
+  const int2 *tile_boxes;                // [ntiles] box range of the tile's frame
+  // binning
+  BinDev bin;
+  const int16_t *labels_in;  // labels for GV_OCC_LABELLED when not fusing in the same pass
+  unsigned long long *ends;  // per cell: low 32 = beams ending here, high 32 = of which hits
+  int32_t *cell_out;         // nullable
+  uint8_t *flags_out;        // nullable
+  unsigned long long *stat_beams;
+};
+
+// ----------------------------------------------------------------------------------
+// device helpers — each mirrors one oracle function (oracle/gv_oracle.c) op for op
+// ----------------------------------------------------------------------------------
+__device__ __forceinline__ bool finitef(float v)
+{
+  return (__float_as_uint(v) & 0x7f800000u) != 0x7f800000u;
+}
+__device__ __forceinline__ bool finite3(float x, float y, float z)
+{
+  return finitef(x) && finitef(y) && finitef(z);
+}
+
+// R1: PCL Transformer<float>::se3 (SSE2): out = c0*x + (c1*y + (c2*z + c3)); call site
+// ref: src/grid_vision_node.cpp:304.
+__device__ __forceinline__ void se3(const float *T, float x, float y, float z, float &ox,
+                                    float &oy, float &oz)
+{
+  ox = __fadd_rn(__fmul_rn(T[0], x),
+                 __fadd_rn(__fmul_rn(T[1], y), __fadd_rn(__fmul_rn(T[2], z), T[3])));
+  oy = __fadd_rn(__fmul_rn(T[4], x),
+                 __fadd_rn(__fmul_rn(T[5], y), __fadd_rn(__fmul_rn(T[6], z), T[7])));
+  oz = __fadd_rn(__fmul_rn(T[8], x),
+                 __fadd_rn(__fmul_rn(T[9], y), __fadd_rn(__fmul_rn(T[10], z), T[11])));
+}
+
+// R3/R4 projection, ref: src/cloud_detections.cpp:268-273 and :19-24.
+//   img = K * (double)(x,y,z), accumulated (a0*b0 + a1*b1) + a2*b2;  u = (float)(img.x/img.z)
+// Canonical K (zero skew, bottom row 0 0 1, float-valued entries — the only K the
+// reference can build, ref: src/object_detection.cpp:241-247 fed from float CAMParams):
+// fx*X and cx*Z are exact in double, the 0*Y term is a signed zero, so
+// img.x = RN(fx*X + cx*Z) = fma(fx, X, cx*Z) unless the sum is zero (sign-of-zero games),
+// in which case the generic path is taken.  img.z = Z exactly for finite X, Y.
+__device__ __forceinline__ void project_point(const CamDev &c, float xf, float yf, float zf,
+                                              float &u, float &v)
+{
+  const double X = (double)xf, Y = (double)yf, Z = (double)zf;
+  double ix, iy, iz;
+  bool generic = !c.canon;
+  if (!generic) {
+    ix = __fma_rn(c.K[0], X, __dmul_rn(c.K[2], Z));
+    iy = __fma_rn(c.K[4], Y, __dmul_rn(c.K[5], Z));
+    iz = Z;
+    generic = (ix == 0.0) || (iy == 0.0) || !finitef(xf) || !finitef(yf);
+  }
+  if (generic) {
+    ix = __dadd_rn(__dadd_rn(__dmul_rn(c.K[0], X), __dmul_rn(c.K[1], Y)), __dmul_rn(c.K[2], Z));
+    iy = __dadd_rn(__dadd_rn(__dmul_rn(c.K[3], X), __dmul_rn(c.K[4], Y)), __dmul_rn(c.K[5], Z));
+    iz = __dadd_rn(__dadd_rn(__dmul_rn(c.K[6], X), __dmul_rn(c.K[7], Y)), __dmul_rn(c.K[8], Z));
+  }
+  u = __double2float_rn(__ddiv_rn(ix, iz));
+  v = __double2float_rn(__ddiv_rn(iy, iz));
+}
+
+// grid_map getIndexFromPosition restatement (oracle gvo_index_coord / gvo_grid_get_index).
+__device__ __forceinline__ double index_coord(double p, double half, double pos, double res)
+{
+  return -__ddiv_rn(__dsub_rn(__dsub_rn(p, half), pos), res);
+}
+
+__device__ __forceinline__ bool grid_get_index(const GridGeom &g, double px, double py, int &ix,
+                                               int &iy)
+{
+  const double qx = -__dsub_rn(__dsub_rn(px, g.pos_x), g.half_x);
+  const double qy = -__dsub_rn(__dsub_rn(py, g.pos_y), g.half_y);
+  if (!(qx >= 0.0 && qy >= 0.0 && qx < g.len_x && qy < g.len_y)) return false;
+  const double ax = index_coord(px, g.half_x, g.pos_x, g.res);
+  const double ay = index_coord(py, g.half_y, g.pos_y, g.res);
+  const int i = __double2int_rz(ax);
+  const int j = __double2int_rz(ay);
+  if (!(i >= 0 && j >= 0 && i < g.nx && j < g.ny)) return false;
+  ix = i;
+  iy = j;
+  return true;
+}
+
+// oracle gvo_clip_end: parametric clip in continuous index space, fixed op order.
+__device__ __forceinline__ void clip_end(double oax, double oay, double eax, double eay, int nx,
+                                         int ny, int &ex, int &ey)
+{
+  const double nxd = (double)nx, nyd = (double)ny;
+  const double dax = __dsub_rn(eax, oax), day = __dsub_rn(eay, oay);
+  double t = 1.0;
+  if (eax < 0.0) {
+    const double tt = __ddiv_rn(__dsub_rn(0.0, oax), dax);
+    if (tt < t) t = tt;
+  } else if (eax >= nxd) {
+    const double tt = __ddiv_rn(__dsub_rn(nxd, oax), dax);
+    if (tt < t) t = tt;
+  }
+  if (eay < 0.0) {
+    const double tt = __ddiv_rn(__dsub_rn(0.0, oay), day);
+    if (tt < t) t = tt;
+  } else if (eay >= nyd) {
+    const double tt = __ddiv_rn(__dsub_rn(nyd, oay), day);
+    if (tt < t) t = tt;
+  }
+  const double cx = __dadd_rn(oax, __dmul_rn(t, dax));
+  const double cy = __dadd_rn(oay, __dmul_rn(t, day));
+  ex = cx < 0.0 ? 0 : (cx >= nxd ? nx - 1 : __double2int_rz(cx));
+  ey = cy < 0.0 ? 0 : (cy >= nyd ? ny - 1 : __double2int_rz(cy));
+}
+
+// X1: one beam -> (end cell, flags).  Mirrors the per-point body of oracle gvo_accumulate.
+__device__ __forceinline__ void bin_point(const BinDev &b, float x, float y, float z, int label,
+                                          int &cell, unsigned &flags)
+{
+  cell = -1;
+  flags = 0;
+  if (!b.origin_ok) return;
+  if (!finite3(x, y, z)) return;
+  float bx, by, bz;
+  se3(b.T, x, y, z, bx, by, bz);
+  if (!finite3(bx, by, bz)) return;
+  double px = (double)bx, py = (double)by;
+  bool hit_ok = true;
+  flags = 1u;  // GV_F_VALID
+  if (b.cap) {
+    const double dx = __dsub_rn(px, b.ox), dy = __dsub_rn(py, b.oy);
+    const double r2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+    if (r2 > b.rmax2) {
+      const double s = __ddiv_rn(b.r_max, __dsqrt_rn(r2));
+      px = __dadd_rn(b.ox, __dmul_rn(s, dx));
+      py = __dadd_rn(b.oy, __dmul_rn(s, dy));
+      hit_ok = false;
+      flags |= 8u;  // GV_F_RANGECAP
+    }
+  }
+  int ex, ey;
+  if (!grid_get_index(b.g, px, py, ex, ey)) {
+    const double eax = index_coord(px, b.g.half_x, b.g.pos_x, b.g.res);
+    const double eay = index_coord(py, b.g.half_y, b.g.pos_y, b.g.res);
+    clip_end(b.oax, b.oay, eax, eay, b.g.nx, b.g.ny, ex, ey);
+    hit_ok = false;
+    flags |= 4u;  // GV_F_CLIPPED
+  }
+  if (hit_ok && b.use_z_gate && !(bz >= b.z_min && bz <= b.z_max)) hit_ok = false;
+  if (hit_ok && b.occ_mode == 1 && !(label >= 0)) hit_ok = false;
+  if (hit_ok) flags |= 2u;  // GV_F_HIT
+  cell = ex + ey * b.g.nx;
+}
+
+// ----------------------------------------------------------------------------------
+// K1/K2: fused transform + project + box-label (+ base transform + cell + bin).
+// One CTA = one tile of 1024 consecutive points of one frame; one thread = 4 consecutive
+// points (three 128-bit loads when aligned).  The frame's detection boxes are staged in
+// shared memory and read with broadcast LDS.128.
+// ----------------------------------------------------------------------------------
+template <bool FUSE, bool BIN>
+__global__ void __launch_bounds__(kThreads) k_points(const __grid_constant__ PointArgs a)
+{
+  extern __shared__ float4 s_box[];
+  __shared__ unsigned s_beams[kThreads / 32];
+
+  unsigned long long start, end;
+  int bb = 0, be = 0;
+  const unsigned tile = blockIdx.x + a.tile0;
+  if (a.nframes > 0) {
+    start = a.tile_start[tile];
+    end = a.tile_end[tile];
+    const int2 br = a.tile_boxes[tile];
+    bb = br.x;
+    be = br.y;
+  } else {
+    start = (unsigned long long)tile * kTilePts;
+    end = a.n;
+  }
+  if (end > start + kTilePts) end = start + kTilePts;
+
+  if (FUSE) {
+    // stage boxes: batch mode -> this frame's list; otherwise every camera's list
+    const int b0 = a.nframes > 0 ? bb : 0;
+    const int b1 = a.nframes > 0 ? be : a.cam[a.ncam - 1].box_end;
+    for (int i = b0 + threadIdx.x; i < b1; i += kThreads) s_box[i - b0] = a.boxes[i];
+    __syncthreads();
+  }
+
+  const unsigned long long i0 = start + (unsigned long long)threadIdx.x * kPtsPerThread;
+  float px[4], py[4], pz[4];
+  bool live[4];
+  if (a.vec_ok && ((i0 & 3ull) == 0) && i0 + 4 <= end) {
+    const float4 vx = __ldg(reinterpret_cast<const float4 *>(a.x + i0));
+    const float4 vy = __ldg(reinterpret_cast<const float4 *>(a.y + i0));
+    const float4 vz = __ldg(reinterpret_cast<const float4 *>(a.z + i0));
+    px[0] = vx.x; px[1] = vx.y; px[2] = vx.z; px[3] = vx.w;
+    py[0] = vy.x; py[1] = vy.y; py[2] = vy.z; py[3] = vy.w;
+    pz[0] = vz.x; pz[1] = vz.y; pz[2] = vz.z; pz[3] = vz.w;
+    live[0] = live[1] = live[2] = live[3] = true;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      live[j] = i0 + j < end;
+      px[j] = live[j] ? __ldg(a.x + i0 + j) : 0.0f;
+      py[j] = live[j] ? __ldg(a.y + i0 + j) : 0.0f;
+      pz[j] = live[j] ? __ldg(a.z + i0 + j) : 0.0f;
+    }
+  }
+
+  int lab0[4] = {-1, -1, -1, -1};
+
+  if (FUSE) {
+    for (int c = 0; c < a.ncam; ++c) {
+      const CamDev &cam = a.cam[c];
+      float u[4], v[4];
+      int lab[4], pix[4];
+      unsigned pending = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        lab[j] = -1;
+        pix[j] = -1;
+        u[j] = v[j] = __int_as_float(0x7fc00000);
+        if (!live[j]) continue;
+        float X = px[j], Y = py[j], Z = pz[j];
+        // R1 (pcl::transformPointCloud: non-finite points pass through when !is_dense)
+        if (cam.has_T && (a.is_dense || finite3(X, Y, Z))) se3(cam.T, px[j], py[j], pz[j], X, Y, Z);
+        // ref: src/cloud_detections.cpp:264
+        if (!finite3(X, Y, Z) || Z <= 0.001f) continue;
+        project_point(cam, X, Y, Z, u[j], v[j]);
+        // ref: :276  (float vs int -> the int is converted to float)
+        if (u[j] < 0.0f || u[j] >= cam.Wf || v[j] < 0.0f || v[j] >= cam.Hf) continue;
+        pix[j] = (int)v[j] * cam.W + (int)u[j];
+        pending |= 1u << j;
+      }
+      // ref: :280-288 first box in list order wins, inclusive bounds.  The double bounds
+      // were rounded to float on the host (ceil for mins, floor for maxes) so these float
+      // compares decide exactly like the reference's float-vs-double compares.
+      const int b0 = a.nframes > 0 ? bb : cam.box_begin;
+      const int b1 = a.nframes > 0 ? be : cam.box_end;
+      const int sb = a.nframes > 0 ? bb : 0;
+      for (int b = b0; b < b1 && pending; ++b) {
+        const float4 B = s_box[b - sb];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if ((pending >> j) & 1u) {
+            if (u[j] >= B.x && u[j] <= B.z && v[j] >= B.y && v[j] <= B.w) {
+              lab[j] = b - b0;
+              pending &= ~(1u << j);
+            }
+          }
+        }
+      }
+      if (c == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) lab0[j] = lab[j];
+      }
+      const unsigned long long plane = (unsigned long long)c * a.n;
+      if (a.labels) {
+        int16_t *lp = a.labels + plane + i0;
+        if (live[3] && ((reinterpret_cast<uintptr_t>(lp) & 7u) == 0)) {
+          short4 s;
+          s.x = (short)lab[0]; s.y = (short)lab[1]; s.z = (short)lab[2]; s.w = (short)lab[3];
+          *reinterpret_cast<short4 *>(lp) = s;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (live[j]) lp[j] = (int16_t)lab[j];
+        }
+      }
+      if (a.pix) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (live[j]) a.pix[plane + i0 + j] = pix[j];
+      }
+      if (a.uv) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (live[j]) {
+            a.uv[2 * plane + i0 + j] = u[j];
+            a.uv[2 * plane + a.n + i0 + j] = v[j];
+          }
+      }
+    }
+  }
+
+  if (BIN) {
+    unsigned nbeams = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (!live[j]) continue;
+      int label = lab0[j];
+      if (!FUSE && a.labels_in) label = a.labels_in[i0 + j];
+      int cell;
+      unsigned flags;
+      bin_point(a.bin, px[j], py[j], pz[j], label, cell, flags);
+      if (cell >= 0) {
+        // one 64-bit RED per beam: low word counts beams ending in the cell, high word hits
+        atomicAdd(a.ends + cell, (flags & 2u) ? 0x100000001ull : 1ull);
+        ++nbeams;
+      }
+      if (a.cell_out) a.cell_out[i0 + j] = cell;
+      if (a.flags_out) a.flags_out[i0 + j] = (uint8_t)flags;
+    }
+    // per-CTA beam count -> one atomic
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nbeams += __shfl_xor_sync(0xffffffffu, nbeams, o);
+    if ((threadIdx.x & 31) == 0) s_beams[threadIdx.x >> 5] = nbeams;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned t = 0;
+#pragma unroll
+      for (int w = 0; w < kThreads / 32; ++w) t += s_beams[w];
+      if (t) atomicAdd(a.stat_beams, (unsigned long long)t);
+    }
+  }
+}
+
+// per-frame tile table for batch mode: one CTA per frame
+__global__ void k_build_tiles(const unsigned long long *frame_offsets, const int *box_frame_offsets,
+                              const unsigned *tile_prefix, int nframes,
+                              unsigned long long *tile_start, unsigned long long *tile_end,
+                              int2 *tile_boxes)
+{
+  const int f = blockIdx.x;
+  if (f >= nframes) return;
+  const unsigned long long s = frame_offsets[f], e = frame_offsets[f + 1];
+  const unsigned t0 = tile_prefix[f], t1 = tile_prefix[f + 1];
+  const int2 br = make_int2(box_frame_offsets[f], box_frame_offsets[f + 1]);
+  for (unsigned t = t0 + threadIdx.x; t < t1; t += blockDim.x) {
+    tile_start[t] = s + (unsigned long long)(t - t0) * kTilePts;
+    tile_end[t] = e;
+    tile_boxes[t] = br;
+  }
+}
+
+// N4: pcl::PointXYZI 32-byte AoS -> SoA planes (ref: pcl::fromROSMsg output consumed at
+// src/grid_vision_node.cpp:103-106,157)
+__global__ void __launch_bounds__(kThreads) k_aos32_to_soa(const float4 *__restrict__ pts,
+                                                           unsigned long long n,
+                                                           float *__restrict__ x,
+                                                           float *__restrict__ y,
+                                                           float *__restrict__ z)
+{
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = __ldg(pts + 2 * i);  // first 16 bytes of the record: x, y, z, w
+  x[i] = p.x;
+  y[i] = p.y;
+  z[i] = p.z;
+}
+
+// R1 alone: GridVision::transformLidarToCamera (ref: src/grid_vision_node.cpp:280-307)
+__global__ void __launch_bounds__(kThreads) k_transform(const float *__restrict__ x,
+                                                        const float *__restrict__ y,
+                                                        const float *__restrict__ z,
+                                                        unsigned long long n, int is_dense,
+                                                        const __grid_constant__ CamDev cam,
+                                                        float *__restrict__ ox,
+                                                        float *__restrict__ oy,
+                                                        float *__restrict__ oz)
+{
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float X = x[i], Y = y[i], Z = z[i];
+  if (is_dense || finite3(X, Y, Z)) se3(cam.T, x[i], y[i], z[i], X, Y, Z);
+  ox[i] = X;
+  oy[i] = Y;
+  oz[i] = Z;
+}
+
+// ----------------------------------------------------------------------------------
+// R4: buildKDTree projection loop (ref: src/cloud_detections.cpp:13-33) with an
+// order-preserving compaction: count pass -> exclusive scan of CTA counts -> scatter pass.
+// ----------------------------------------------------------------------------------
+__device__ __forceinline__ bool kd_keep(const CamDev &cam, int is_dense, float x, float y, float z,
+                                        float &X, float &Y, float &Z)
+{
+  X = x; Y = y; Z = z;
+  if (cam.has_T && (is_dense || finite3(x, y, z))) se3(cam.T, x, y, z, X, Y, Z);
+  return !(Z <= 0.0f);  // ref: :16  if(p.z <= 0) continue;   (NaN depth passes)
+}
+
+__global__ void __launch_bounds__(kThreads) k_kdtree_count(const float *__restrict__ x,
+                                                           const float *__restrict__ y,
+                                                           const float *__restrict__ z,
+                                                           unsigned long long n, int is_dense,
+                                                           const __grid_constant__ CamDev cam,
+                                                           unsigned *__restrict__ cta_count)
+{
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  float X, Y, Z;
+  const bool keep = i < n && kd_keep(cam, is_dense, x[i], y[i], z[i], X, Y, Z);
+  const int c = __syncthreads_count(keep);
+  if (threadIdx.x == 0) cta_count[blockIdx.x] = (unsigned)c;
+}
+
+__global__ void __launch_bounds__(kThreads) k_kdtree_scatter(const float *__restrict__ x,
+                                                             const float *__restrict__ y,
+                                                             const float *__restrict__ z,
+                                                             unsigned long long n, int is_dense,
+                                                             const __grid_constant__ CamDev cam,
+                                                             const unsigned *__restrict__ cta_base,
+                                                             float *__restrict__ uvz)
+{
+  __shared__ unsigned s_warp[kThreads / 32];
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  float X, Y, Z;
+  const bool keep = i < n && kd_keep(cam, is_dense, x[i], y[i], z[i], X, Y, Z);
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned m = __ballot_sync(0xffffffffu, keep);
+  if (lane == 0) s_warp[warp] = __popc(m);
+  __syncthreads();
+  unsigned base = cta_base[blockIdx.x];
+  for (unsigned w = 0; w < warp; ++w) base += s_warp[w];
+  if (keep) {
+    const unsigned long long o = (unsigned long long)base + __popc(m & ((1u << lane) - 1u));
+    float u, v;
+    project_point(cam, X, Y, Z, u, v);
+    uvz[3 * o + 0] = u;
+    uvz[3 * o + 1] = v;
+    uvz[3 * o + 2] = Z;
+  }
+}
+
+// in-place exclusive scan of up to 1024*blockDim chunks: level kernel (CTA scans 1024
+// values, emits its total) — composed recursively on the host (scan_u32)
+__global__ void __launch_bounds__(1024) k_scan_block(unsigned *data, unsigned long long n,
+                                                     unsigned *block_sums)
+{
+  __shared__ unsigned s_w[32];
+  const unsigned long long i = (unsigned long long)blockIdx.x * 1024 + threadIdx.x;
+  const unsigned v = i < n ? data[i] : 0u;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= (unsigned)o) incl += t;
+  }
+  if (lane == 31) s_w[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned w = s_w[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= (unsigned)o) w += t;
+    }
+    s_w[lane] = w;  // inclusive over warps
+  }
+  __syncthreads();
+  const unsigned warp_base = warp ? s_w[warp - 1] : 0u;
+  if (i < n) data[i] = warp_base + incl - v;
+  if (threadIdx.x == 1023 && block_sums) block_sums[blockIdx.x] = warp_base + incl;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_add(unsigned *data, unsigned long long n,
+                                                   const unsigned *block_base)
+{
+  const unsigned long long i = (unsigned long long)blockIdx.x * 1024 + threadIdx.x;
+  if (i < n) data[i] += block_base[blockIdx.x];
+}
+
+// ----------------------------------------------------------------------------------
+// stable partition of point indices by label (R3's per-box push_back order,
+// ref: src/cloud_detections.cpp:280-297): histogram -> scan -> ranked scatter
+// ----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_label_hist(const int16_t *__restrict__ labels,
+                                                         unsigned long long n, int nboxes,
+                                                         unsigned nblocks,
+                                                         unsigned *__restrict__ hist)
+{
+  extern __shared__ unsigned s_h[];
+  for (int b = threadIdx.x; b < nboxes; b += kThreads) s_h[b] = 0;
+  __syncthreads();
+  const unsigned long long i = (unsigned long long)blockIdx.x * kThreads + threadIdx.x;
+  if (i < n) {
+    const int l = labels[i];
+    if (l >= 0 && l < nboxes) atomicAdd(&s_h[l], 1u);
+  }
+  __syncthreads();
+  // label-major layout so one exclusive scan yields box-concatenated output offsets
+  for (int b = threadIdx.x; b < nboxes; b += kThreads)
+    hist[(unsigned long long)b * nblocks + blockIdx.x] = s_h[b];
+}
+
+__global__ void __launch_bounds__(kThreads) k_label_scatter(const int16_t *__restrict__ labels,
+                                                            unsigned long long n, int nboxes,
+                                                            unsigned nblocks,
+                                                            const unsigned *__restrict__ base,
+                                                            unsigned *__restrict__ indices)
+{
+  extern __shared__ unsigned s_cnt[];  // [8 warps][nboxes] -> exclusive over warps
+  constexpr int kWarps = kThreads / 32;
+  for (int b = threadIdx.x; b < nboxes * kWarps; b += kThreads) s_cnt[b] = 0;
+  __syncthreads();
+  const unsigned long long i = (unsigned long long)blockIdx.x * kThreads + threadIdx.x;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int l = -1;
+  if (i < n) {
+    l = labels[i];
+    if (l >= nboxes) l = -1;
+  }
+  const unsigned peers = __match_any_sync(0xffffffffu, l);
+  const unsigned rank = __popc(peers & ((1u << lane) - 1u));
+  if (l >= 0 && rank == 0) s_cnt[warp * nboxes + l] = __popc(peers);
+  __syncthreads();
+  for (int b = threadIdx.x; b < nboxes; b += kThreads) {
+    unsigned run = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+      const unsigned c = s_cnt[w * nboxes + b];
+      s_cnt[w * nboxes + b] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+  if (l >= 0) {
+    const unsigned o =
+      base[(unsigned long long)l * nblocks + blockIdx.x] + s_cnt[warp * nboxes + l] + rank;
+    indices[o] = (unsigned)i;
+  }
+}
+
+// ----------------------------------------------------------------------------------
+// K3: de-duplicated raycast.  All beams binned since the last flush share one start
+// cell, and a Bresenham line is a pure function of (start, end), so the traversed-cell
+// multiset of the whole batch is  sum over distinct end cells e of  w_e * line(start, e).
+//   pass A  compact the non-zero entries of the ends plane into a list, settle the end
+//           cells themselves (hit += high word, miss += low - high), clear the plane
+//   pass B  walk each listed line once, adding w_e to every cell before the end
+// ----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_ends_compact(unsigned long long *__restrict__ ends,
+                                                           unsigned long long ncells,
+                                                           int32_t *__restrict__ hit,
+                                                           int32_t *__restrict__ miss,
+                                                           uint2 *__restrict__ list,
+                                                           unsigned *__restrict__ list_count,
+                                                           unsigned rank, unsigned world)
+{
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  // all lanes of a warp iterate together (bound rounded up to a warp multiple)
+  const unsigned long long nround = (ncells + 31ull) & ~31ull;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nround;
+       i += stride) {
+    unsigned long long e = i < ncells ? ends[i] : 0ull;
+    if (e != 0ull) ends[i] = 0ull;
+    // multi-GPU (gv_grid_finalize_multi): every rank holds the all-reduced plane and owns
+    // the end cells with lin % world == rank; ownership by CELL, not by list position,
+    // because the append order below differs from rank to rank.
+    const bool nz = e != 0ull && (world == 1u || (unsigned)(i % world) == rank);
+    const unsigned m = __ballot_sync(0xffffffffu, nz);
+    if (m == 0) continue;
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(list_count, (unsigned)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (nz) {
+      const unsigned total = (unsigned)(e & 0xffffffffull);
+      const unsigned hits = (unsigned)(e >> 32);
+      list[base + __popc(m & ((1u << lane) - 1u))] = make_uint2((unsigned)i, total);
+      if (hits) hit[i] += (int32_t)hits;
+      if (total - hits) miss[i] += (int32_t)(total - hits);
+    }
+  }
+}
+
+// grid_map LineIterator restatement (oracle gvo_line_init / gvo_line_step)
+struct Line {
+  int x, y, inc1x, inc1y, inc2x, inc2y, den, num, add, n;
+};
+
+__device__ __forceinline__ void line_init(Line &L, int sx, int sy, int ex, int ey)
+{
+  const int dx = ex >= sx ? ex - sx : sx - ex;
+  const int dy = ey >= sy ? ey - sy : sy - ey;
+  L.x = sx;
+  L.y = sy;
+  L.inc1x = L.inc2x = ex >= sx ? 1 : -1;
+  L.inc1y = L.inc2y = ey >= sy ? 1 : -1;
+  if (dx >= dy) {
+    L.inc1x = 0; L.inc2y = 0;
+    L.den = dx; L.num = dx / 2; L.add = dy; L.n = dx + 1;
+  } else {
+    L.inc2x = 0; L.inc1y = 0;
+    L.den = dy; L.num = dy / 2; L.add = dx; L.n = dy + 1;
+  }
+}
+
+__device__ __forceinline__ void line_step(Line &L)
+{
+  L.num += L.add;
+  if (L.num >= L.den) {
+    L.num -= L.den;
+    L.x += L.inc1x;
+    L.y += L.inc1y;
+  }
+  L.x += L.inc2x;
+  L.y += L.inc2y;
+}
+
+__global__ void __launch_bounds__(kThreads) k_raycast_lines(const uint2 *__restrict__ list,
+                                                            const unsigned *__restrict__ list_count,
+                                                            int sx, int sy, int nx,
+                                                            int32_t *__restrict__ miss,
+                                                            unsigned long long *__restrict__ stats)
+{
+  const unsigned count = *list_count;
+  unsigned long long logical = 0, physical = 0, lines = 0;
+  const unsigned stride = gridDim.x * blockDim.x;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+    const uint2 e = list[i];
+    const int ex = (int)(e.x % (unsigned)nx), ey = (int)(e.x / (unsigned)nx);
+    Line L;
+    line_init(L, sx, sy, ex, ey);
+    for (int k = 0; k + 1 < L.n; ++k) {
+      atomicAdd(miss + (L.x + L.y * nx), (int32_t)e.y);
+      line_step(L);
+    }
+    logical += (unsigned long long)e.y * (unsigned long long)L.n;
+    physical += (unsigned long long)(L.n - 1);
+    lines += 1;
+  }
+  // warp-reduce the three counters, one atomic each per warp
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    logical += __shfl_xor_sync(0xffffffffu, logical, o);
+    physical += __shfl_xor_sync(0xffffffffu, physical, o);
+    lines += __shfl_xor_sync(0xffffffffu, lines, o);
+  }
+  if ((threadIdx.x & 31) == 0 && lines) {
+    atomicAdd(stats + 0, logical);
+    atomicAdd(stats + 1, physical);
+    atomicAdd(stats + 2, lines);
+  }
+}
+
+// ----------------------------------------------------------------------------------
+// R8/R9 footprints -> index rectangles (ref: src/occupancy_grid.cpp:72-93,107-138,140-172)
+// mode 0: explicit corners n x 8; 1: poses n x (x,y,length,width) (:79-90);
+// mode 2: points n x (x,y) + class label (:107-138 with :185-196)
+// rect = (min_ix, min_iy, max_ix, max_iy); skipped footprints get an empty rect.
+// ----------------------------------------------------------------------------------
+__device__ __forceinline__ float estimated_depth(int label)
+{
+  switch (label) {  // ref: src/occupancy_grid.cpp:185-196
+  case 9: return 3.5f;  // VEHICLE
+  case 2: return 0.6f;  // PERSON
+  case 0: return 2.5f;  // BIKE
+  case 1: return 2.5f;  // MOTORBIKE
+  default: return -1.0f;
+  }
+}
+
+__global__ void k_footprint_rects(const double *__restrict__ in, const int32_t *__restrict__ labels,
+                                  int n, int mode, const __grid_constant__ GridGeom g,
+                                  int4 *__restrict__ rects)
+{
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  double c[8];
+  if (mode == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c[i] = in[8 * k + i];
+  } else if (mode == 1) {
+    const double x = in[4 * k], y = in[4 * k + 1], L = in[4 * k + 2], W = in[4 * k + 3];
+    const double hl = __ddiv_rn(L, 2.0), hw = __ddiv_rn(W, 2.0);
+    const double xf = __dadd_rn(x, hl), xb = __dsub_rn(x, hl);
+    const double yl = __dsub_rn(y, hw), yr = __dadd_rn(y, hw);
+    c[0] = xb; c[1] = yl; c[2] = xf; c[3] = yl; c[4] = xf; c[5] = yr; c[6] = xb; c[7] = yr;
+  } else {
+    const double x = in[2 * k], y = in[2 * k + 1];
+    const float d = estimated_depth(labels[k]);
+    const double dd = (double)d, dh = (double)__fdiv_rn(d, 2.0f);
+    c[0] = __dadd_rn(x, dd); c[1] = __dadd_rn(y, dh);
+    c[2] = __dadd_rn(x, dd); c[3] = __dsub_rn(y, dh);
+    c[4] = x;                c[5] = __dsub_rn(y, dh);
+    c[6] = x;                c[7] = __dadd_rn(y, dh);
+  }
+  int minx = 0, miny = 0, maxx = -1, maxy = -1;
+  bool valid = true;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int ix, iy;
+    if (!grid_get_index(g, c[2 * i], c[2 * i + 1], ix, iy)) {  // ref: :152-156
+      valid = false;
+      break;
+    }
+    if (i == 0) {
+      minx = maxx = ix;
+      miny = maxy = iy;
+    } else {
+      minx = min(minx, ix); miny = min(miny, iy);
+      maxx = max(maxx, ix); maxy = max(maxy, iy);
+    }
+  }
+  rects[k] = valid ? make_int4(minx, miny, maxx, maxy) : make_int4(1, 1, 0, 0);
+}
+
+// grid_map getIndex for host-supplied positions (parity hook)
+__global__ void k_get_index(const double *__restrict__ xy, int n, const __grid_constant__ GridGeom g,
+                            int32_t *__restrict__ out)
+{
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  int ix = -1, iy = -1;
+  if (!grid_get_index(g, xy[2 * k], xy[2 * k + 1], ix, iy)) ix = iy = -1;
+  out[2 * k] = ix;
+  out[2 * k + 1] = iy;
+}
+
+// ----------------------------------------------------------------------------------
+// K4: finalise — one streaming pass over the grid.
+//   l += k_decay*(-0.2f); l += miss*(-0.4f); l += hit*1.2f; +0.85f per covering footprint;
+//   clamp [-2, 3.6]; occupancy = 1/(1+exp(-l)); counts cleared.
+// R7 (ref: src/occupancy_grid.cpp:16-31) is COUNTS=false, nfoot=0, k_decay=1;
+// R8/R9 (ref: :65-105, :33-63) add the footprint rectangles.  Adding the same constant
+// 0.85f once per covering footprint is order-independent, so only the cover count is
+// needed to reproduce the reference's sequential block adds bit for bit.
+// cell0/ncell select a slab (multi-GPU: each rank finalises its own slab).
+// ----------------------------------------------------------------------------------
+struct FinalizeArgs {
+  float *log_odds, *occupancy;
+  int32_t *hit, *miss;
+  unsigned long long cell0, ncell;  // slab [cell0, cell0+ncell), cell0 % 4 == 0
+  int nx;
+  float decay;  // (float)k_decay * -0.2f, computed on the host in float
+  const int4 *rects;
+  int nfoot;
+};
+
+template <bool COUNTS>
+__global__ void __launch_bounds__(kThreads) k_finalize(const __grid_constant__ FinalizeArgs a)
+{
+  __shared__ int4 s_rect[kMaxFootCand];
+  __shared__ int s_nc;
+  const unsigned long long blk0 = a.cell0 + (unsigned long long)blockIdx.x * (kThreads * 4);
+  if (a.nfoot > 0) {
+    if (threadIdx.x == 0) s_nc = 0;
+    __syncthreads();
+    unsigned long long blk1 = blk0 + kThreads * 4 - 1;
+    const unsigned long long last = a.cell0 + a.ncell - 1;
+    if (blk1 > last) blk1 = last;
+    const int iy0 = (int)(blk0 / (unsigned)a.nx), iy1 = (int)(blk1 / (unsigned)a.nx);
+    for (int r = threadIdx.x; r < a.nfoot; r += kThreads) {
+      const int4 R = a.rects[r];
+      if (R.z >= R.x && R.w >= iy0 && R.y <= iy1) {
+        const int slot = atomicAdd(&s_nc, 1);
+        if (slot < kMaxFootCand) s_rect[slot] = R;
+      }
+    }
+    __syncthreads();
+  }
+  const int ncand = a.nfoot > 0 ? s_nc : 0;
+
+  const unsigned long long i0 = blk0 + (unsigned long long)threadIdx.x * 4;
+  const unsigned long long endc = a.cell0 + a.ncell;
+  if (i0 >= endc) return;
+  const bool full = i0 + 4 <= endc;
+  float l[4];
+  int h[4] = {0, 0, 0, 0}, m[4] = {0, 0, 0, 0};
+  if (full) {
+    const float4 v = *reinterpret_cast<const float4 *>(a.log_odds + i0);
+    l[0] = v.x; l[1] = v.y; l[2] = v.z; l[3] = v.w;
+    if (COUNTS) {
+      const int4 hv = *reinterpret_cast<const int4 *>(a.hit + i0);
+      const int4 mv = *reinterpret_cast<const int4 *>(a.miss + i0);
+      h[0] = hv.x; h[1] = hv.y; h[2] = hv.z; h[3] = hv.w;
+      m[0] = mv.x; m[1] = mv.y; m[2] = mv.z; m[3] = mv.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool ok = i0 + j < endc;
+      l[j] = ok ? a.log_odds[i0 + j] : 0.0f;
+      if (COUNTS && ok) {
+        h[j] = a.hit[i0 + j];
+        m[j] = a.miss[i0 + j];
+      }
+    }
+  }
+  int ix = (int)(i0 % (unsigned)a.nx), iy = (int)(i0 / (unsigned)a.nx);
+  float o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float v = __fadd_rn(l[j], a.decay);
+    if (COUNTS) {
+      v = __fadd_rn(v, __fmul_rn((float)m[j], -0.4f));  // log_odds_free_  (occupancy_grid.hpp:25)
+      v = __fadd_rn(v, __fmul_rn((float)h[j], 1.2f));   // log_odds_occupied_ (:26)
+    }
+    if (ncand) {
+      int cover = 0;
+      if (ncand <= kMaxFootCand) {
+        for (int r = 0; r < ncand; ++r) {
+          const int4 R = s_rect[r];
+          cover += (ix >= R.x && ix <= R.z && iy >= R.y && iy <= R.w) ? 1 : 0;
+        }
+      } else {  // candidate list overflowed: scan every footprint
+        for (int r = 0; r < a.nfoot; ++r) {
+          const int4 R = a.rects[r];
+          cover += (ix >= R.x && ix <= R.z && iy >= R.y && iy <= R.w) ? 1 : 0;
+        }
+      }
+      for (int r = 0; r < cover; ++r) v = __fadd_rn(v, 0.85f);  // ref: occupancy_grid.cpp:182
+    }
+    v = v < -2.0f ? -2.0f : v;  // cwiseMax(min_log_odds_)  ref: :21-22
+    v = v > 3.6f ? 3.6f : v;    // cwiseMin(max_log_odds_)
+    l[j] = v;
+    o[j] = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-v)));  // ref: :28
+    if (++ix == a.nx) {
+      ix = 0;
+      ++iy;
+    }
+  }
+  if (full) {
+    *reinterpret_cast<float4 *>(a.log_odds + i0) = make_float4(l[0], l[1], l[2], l[3]);
+    *reinterpret_cast<float4 *>(a.occupancy + i0) = make_float4(o[0], o[1], o[2], o[3]);
+    if (COUNTS) {
+      *reinterpret_cast<int4 *>(a.hit + i0) = make_int4(0, 0, 0, 0);
+      *reinterpret_cast<int4 *>(a.miss + i0) = make_int4(0, 0, 0, 0);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (i0 + j < endc) {
+        a.log_odds[i0 + j] = l[j];
+        a.occupancy[i0 + j] = o[j];
+        if (COUNTS) {
+          a.hit[i0 + j] = 0;
+          a.miss[i0 + j] = 0;
+        }
+      }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_fill_f32(float *p, unsigned long long n, float v)
+{
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += stride)
+    p[i] = v;
+}
+
+// N3: nav_msgs/OccupancyGrid cells (grid_map_ros toOccupancyGrid(grid,"occupancy",0,1,msg),
+// call site ref: src/grid_vision_node.cpp:270): reversed linear order, float -> int8.
+__global__ void __launch_bounds__(kThreads) k_to_occupancy(const float *__restrict__ occ,
+                                                           unsigned long long nc,
+                                                           int8_t *__restrict__ data)
+{
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nc) return;
+  float value = __fdiv_rn(__fsub_rn(occ[i], 0.0f), __fsub_rn(1.0f, 0.0f));
+  if (value != value) value = -1.0f;
+  else {
+    float c = value < 0.0f ? 0.0f : value;
+    c = c > 1.0f ? 1.0f : c;
+    value = __fadd_rn(0.0f, __fmul_rn(c, 100.0f));
+  }
+  data[nc - i - 1] = (int8_t)value;
+}
+
+// ref: src/cloud_detections.cpp:282-283 compares float u,v (promoted) against the double box
+// bounds, inclusive.  u >= x_min  <=>  u >= RU_f32(x_min)  and  u <= x_max  <=>  u <= RD_f32(x_max)
+// for every float u, so rounding the bounds once (toward +inf for mins, -inf for maxes) turns
+// the per-point double compares into exact float compares.  NaN bounds stay NaN (never match).
+struct BoxRaw {  // ref: include/grid_vision/object_detection.hpp:27-32 (40 bytes)
+  double x_min, y_min, x_max, y_max;
+  float confidence;
+  int label;
+};
+
+__global__ void k_round_boxes(const BoxRaw *__restrict__ in, int n, float4 *__restrict__ out)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = make_float4(__double2float_ru(in[i].x_min), __double2float_ru(in[i].y_min),
+                       __double2float_rd(in[i].x_max), __double2float_rd(in[i].y_max));
+}
+
+// sensor origin -> start cell and continuous index coordinates (single thread)
+struct OriginOut {
+  double oax, oay;
+  int sx, sy, ok, pad;
+};
+
+__global__ void k_origin_setup(double ox, double oy, const __grid_constant__ GridGeom g,
+                               OriginOut *out)
+{
+  OriginOut o;
+  o.sx = o.sy = -1;
+  o.pad = 0;
+  o.ok = grid_get_index(g, ox, oy, o.sx, o.sy) ? 1 : 0;
+  o.oax = index_coord(ox, g.half_x, g.pos_x, g.res);
+  o.oay = index_coord(oy, g.half_y, g.pos_y, g.res);
+  *out = o;
+}
+
+}  // namespace gv
