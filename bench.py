@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py — points/sec through project + bbox-fuse + grid-update (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--frames F]
+
+Workload: BASELINE.json configs[2] ("C3"): a batch of F synthetic 64-beam scans (131 072
+points each, default F = 4096 -> 5.37e8 points) with 50 synthetic YOLO boxes per scan, one
+416x416 camera, fused into one 2048x2048 @0.1 m log-odds grid.  Frames are sharded across
+the N ranks (strong scaling: the whole job is F frames at every N) and the grid is merged
+by the exact integer NCCL reduction inside gv_grid_finalize_multi.
+
+One "step" = the whole hot path over the batch:
+  K1/K2 fused kernel (transform -> project -> label -> base transform -> cell -> bin),
+  K3 de-duplicated raycast, [NCCL merge], K4 finalise (log-odds, clamp, sigmoid).
+`value` is timed with inputs resident in HBM; `e2e` goes through the host-pointer C-ABI
+calls (gv_process_batch + gv_grid_finalize[_multi] + gv_grid_download) with pinned host
+buffers, H2D/D2H inside the timed region.
+
+--impl reference times the CPU oracle port (oracle/, the restatement of the reference's CPU
+path; the reference itself cannot be built here: no ROS 2 / PCL / Eigen / grid_map) on all
+host threads, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "points/sec through project+bbox-fuse+grid-update"
+UNIT = "points/s"
+B_PT = 14   # algorithmic bytes per point: read x,y,z (12) + write int16 label (2)   SURVEY §8.d
+B_CELL = 12  # algorithmic bytes per grid cell: read log_odds, write log_odds + occupancy
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def mark(self):
+        return time.time()
+
+    def stop(self, t0=None, t1=None):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ts, line in self.rows:
+            if t0 is not None and not (t0 - 0.05 <= ts <= t1 + 0.15):
+                continue
+            f = [s.strip() for s in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------- CPU baseline
+def cpu_oracle_run(wl, xyz, boxes_per_frame, threads):
+    """One pass of the oracle port over the frames in xyz ([3, F*P] numpy), frame-parallel with
+    private count grids and an integer merge (BASELINE.md variant 3).  Returns seconds."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from grid_vision_b200 import synth
+    from oracle import gv_oracle as orc
+    P = wl.points_per_frame
+    F = xyz.shape[1] // P
+    Tc = synth.camera_extrinsics(1)[0]
+    Tb = synth.T_base_lidar()
+    K = wl.K()
+    threads = max(1, min(threads, F))
+    grids = [orc.Grid.from_cells(wl.grid_nx, wl.grid_ny, wl.resolution) for _ in range(threads)]
+
+    def work(t):
+        g = grids[t]
+        for f in range(t, F, threads):
+            fx = xyz[:, f * P:(f + 1) * P]
+            cx, cy, cz = orc.transform_points(Tc, fx[0], fx[1], fx[2])
+            lab, _, _, _ = orc.project_label(K, wl.image_w, wl.image_h, cx, cy, cz, boxes_per_frame[f])
+            g.accumulate(Tb, fx[0], fx[1], fx[2], lab, r_max=wl.r_max, want_cells=False)
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(work, range(threads)))
+    for g in grids[1:]:
+        grids[0].hit += g.hit
+        grids[0].miss += g.miss
+    grids[0].finalize(F)
+    return time.perf_counter() - t0
+
+
+def cpu_sample(wl, frames):
+    from grid_vision_b200 import synth
+    xyz = synth.make_scans(wl, frames=frames, device="cpu", chunk=2).numpy()
+    boxes = [synth.make_boxes(wl, frame=f) for f in range(frames)]
+    return xyz, boxes
+
+
+def run_reference_arm(args, wl):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    frames = max(2, min(2 * cores, 64))
+    xyz, boxes = cpu_sample(wl, frames)
+    pts = xyz.shape[1]
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_oracle_run(wl, xyz, boxes, cores)
+    ts = [cpu_oracle_run(wl, xyz, boxes, cores) for _ in range(args.steps)]
+    t = float(np.mean(ts))
+    v = pts / t
+    sample = f"{frames} frames ({pts} points) of the workload per step, frame-parallel on {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32 transform / f64 projection+indices / i32 counts", "data": "synthetic",
+        "config": workload_config(wl, wl.frames, args.gpus, sample=sample),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(wl, frames, gpus, **extra):
+    c = {"workload": f"C3 batched replay: {frames} synthetic 64-beam scans x {wl.points_per_frame} pts, "
+                     f"{wl.boxes_per_camera} boxes/scan, 416x416 camera, {wl.grid_nx}x{wl.grid_ny} grid "
+                     f"@{wl.resolution} m, r_max {wl.r_max} m, batch_sum semantics",
+         "frames": frames, "points": frames * wl.points_per_frame, "cells": wl.cells,
+         "sharding": f"frames split contiguously over {gpus} rank(s); NCCL int merge in finalize",
+         "l2": "inputs larger than L2: each rank streams its resident point planes "
+               "(>= 800 MB at 8 ranks) once per step"}
+    c.update(extra)
+    return c
+
+
+# --------------------------------------------------------------------------- our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=0, help="total frames in the batch (default 4096)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+
+    from grid_vision_b200 import synth
+    wl = synth.C3 if not args.frames else synth.C3.scaled(frames=args.frames)
+    if args.impl == "reference":
+        run_reference_arm(args, wl)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import grid_vision_b200 as gv
+    from grid_vision_b200 import sharding
+
+    rank, world, local = sharding.env_rank_world()
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        print(json.dumps({"error": "launch with torchrun for --gpus > 1"}))
+        sys.exit(2)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    F = wl.frames
+    f0, f1 = sharding.shard_frames(F, rank, world)
+    nf = f1 - f0
+    P = wl.points_per_frame
+    n_local = nf * P
+
+    # ---- synthetic inputs (outside every timed region)
+    xyz = synth.make_scans(wl, frame0=f0, frames=nf, device=dev)
+    boxes_np = np.concatenate([synth.make_boxes(wl, frame=f) for f in range(f0, f1)])
+    d_boxes = torch.from_numpy(boxes_np.view(np.uint8).copy()).to(dev)
+    fo = (np.arange(nf + 1, dtype=np.uint64) * np.uint64(P))
+    bo = (np.arange(nf + 1) * wl.boxes_per_camera).astype(np.int32)
+    d_labels = torch.empty(n_local, dtype=torch.int16, device=dev)
+    prm = gv.accum_params(occ_mode=gv.OCC_ALL, r_max=wl.r_max)
+
+    ctx = gv.Context(local)
+    ctx.use_torch_stream()
+    ctx.set_cameras(wl.K().reshape(1, 9), [[wl.image_w, wl.image_h]], synth.camera_extrinsics(1))
+    ctx.grid_init_cells(wl.grid_nx, wl.grid_ny, wl.resolution)
+    ctx.set_base_transform(synth.T_base_lidar())
+    if world > 1:
+        sharding.init_context_comm(ctx, dev)
+    multi = world > 1
+
+    def step_resident(ev=None):
+        if ev:
+            ev[0].record()
+        ctx.process_batch(xyz[0], xyz[1], xyz[2], fo, d_boxes, bo, prm, d_labels)
+        if ev:
+            ev[1].record()
+        ctx.grid_finalize(nf if not multi else F, multi=multi)
+        if ev:
+            ev[2].record()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    launches0 = ctx.stats()["kernel_launches"]
+    st0 = ctx.stats()
+    sampler = ClockSampler(local) if rank == 0 else None
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    tm0 = sampler.mark() if sampler else None
+    start.record()
+    for k in range(args.steps):
+        step_resident(evs[k])
+    stop.record()
+    barrier()
+    tm1 = sampler.mark() if sampler else None
+    ms_total = max_over_ranks(start.elapsed_time(stop))
+    clocks = sampler.stop(tm0, tm1) if sampler else None
+    st1 = ctx.stats()
+    launches = st1["kernel_launches"] - launches0
+    if world > 1:  # raycast lines are split across ranks: sum the per-rank counters
+        t = torch.tensor([st1[k] - st0[k] for k in ("cells_logical", "cells_physical", "distinct_ends")],
+                         dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        for k, v in zip(("cells_logical", "cells_physical", "distinct_ends"), t.tolist()):
+            st1[k] = st0[k] + int(v)
+    ms_step = ms_total / args.steps
+    value = F * P / (ms_step * 1e-3)
+    ms_points = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
+    ms_final = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
+
+    # ---- end to end through the host-pointer C ABI (pinned host buffers)
+    e2e = None
+    if not args.no_e2e:
+        hx = torch.empty((3, n_local), dtype=torch.float32, pin_memory=True)
+        hx.copy_(xyz)
+        h_boxes = torch.from_numpy(boxes_np.view(np.uint8).copy()).pin_memory()
+        h_labels = torch.empty(n_local, dtype=torch.int16, pin_memory=True)
+        h_lo = torch.empty(wl.cells, dtype=torch.float32, pin_memory=True)
+        h_oc = torch.empty(wl.cells, dtype=torch.float32, pin_memory=True)
+        lo_np, oc_np = h_lo.numpy(), h_oc.numpy()
+        import ctypes as C
+        px, py, pz = (hx[i].data_ptr() for i in range(3))
+
+        def step_e2e():
+            ctx.process_batch_ptrs(px, py, pz, fo, h_boxes.data_ptr(), bo, prm, h_labels.data_ptr())
+            ctx.grid_finalize(nf if not multi else F, multi=multi)
+            ctx._check(ctx._lib.gv_grid_download(ctx._h, C.c_void_p(lo_np.ctypes.data),
+                                                 C.c_void_p(oc_np.ctypes.data)), "gv_grid_download")
+
+        for _ in range(min(args.warmup, 2)):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e_start.record()
+        for _ in range(args.steps):
+            step_e2e()
+        e_stop.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        # the host entry points return synchronously, so host wall time between the two
+        # barriers is the end-to-end time; the device-side events agree to within launch latency
+        ms_e2e = max_over_ranks(max(wall * 1e3, e_start.elapsed_time(e_stop))) / args.steps
+        e2e = {"value": F * P / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+               "h2d_bytes_per_step": int(F * P * 12 + F * wl.boxes_per_camera * 40),
+               "d2h_bytes_per_step": int(F * P * 2 + world * wl.cells * 8),
+               "api": "gv_process_batch + gv_grid_finalize" + ("_multi" if multi else "") +
+                      " + gv_grid_download, pinned host buffers"}
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        pts_bytes = n_local * B_PT
+        achieved = pts_bytes / (ms_points * 1e-3) / 1e9
+        dst = st1["distinct_ends"] - st0["distinct_ends"]
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32 transform / f64 projection+indices / i32 counts", "data": "synthetic",
+            "config": workload_config(wl, F, world),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "gv::k_points<true,true> (fused transform+project+label+bin)",
+                         "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None,
+                         "algorithmic_bytes_per_launch": pts_bytes, "ms_per_launch": ms_points},
+            "phases_ms": {"fuse_bin": ms_points, "raycast_merge_finalize": ms_final},
+            "cells_per_s": {"logical": (st1["cells_logical"] - st0["cells_logical"]) / args.steps / (ms_step * 1e-3),
+                            "physical": (st1["cells_physical"] - st0["cells_physical"]) / args.steps / (ms_step * 1e-3),
+                            "distinct_ends_per_step": dst / args.steps},
+        }
+        if not args.no_cpu and world == 1:
+            cores = os.cpu_count() or 1
+            frames = max(2, min(2 * cores, 64))
+            cx, cb = cpu_sample(wl, frames)
+            t = cpu_oracle_run(wl, cx, cb, cores)
+            out["cpu_baseline"] = {"value": cx.shape[1] / t, "unit": UNIT, "cores": cores, "kind": "port",
+                                   "sample": f"{frames} frames ({cx.shape[1]} points), frame-parallel oracle port, "
+                                             f"{t:.2f} s"}
+        else:
+            out["cpu_baseline"] = None
+        print(json.dumps(out))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
