@@ -31,7 +31,7 @@ enum {
   S_X, S_Y, S_Z, S_AOS, S_LAB, S_PIX, S_UV, S_BOX_RAW, S_BOX_F4, S_FRAME_OFF, S_BOX_OFF,
   S_TILE_PREFIX, S_TILE_START, S_TILE_END, S_TILE_BOX, S_CELL, S_FLAGS, S_FOOT_IN, S_FOOT_LAB,
   S_RECT, S_SMALL, S_OX, S_OY, S_OZ, S_SCAN0, S_SCAN1, S_SCAN2, S_SCAN3, S_UVZ, S_INDICES,
-  S_LABELS_IN, S_COUNT
+  S_LABELS_IN, S_MASKS, S_SET_OFF, S_COUNT
 };
 
 constexpr size_t kPlanePad = 4096;  // slack cells so multi-GPU slabs can be equal-sized
@@ -208,6 +208,26 @@ int upload_boxes(gv_ctx *ctx, const gv_box *boxes, int nboxes, bool on_device, f
   return GV_OK;
 }
 
+// image-tile prefilter geometry: square tiles of 2^shift pixels, at most 16 per axis
+void mask_geometry(int W, int H, int *shift, int *tx, int *ty)
+{
+  int sh = 4;
+  const int m = W > H ? W : H;
+  while (((m + (1 << sh) - 1) >> sh) > 16) ++sh;
+  *shift = sh;
+  *tx = (W + (1 << sh) - 1) >> sh;
+  *ty = (H + (1 << sh) - 1) >> sh;
+}
+
+int tile_points_for(unsigned long long n, int num_sms)
+{
+  // bigger CTA tiles amortise the box/mask staging; small clouds keep every SM busy
+  const unsigned long long per = n / ((unsigned long long)num_sms * 8ull);
+  if (per >= 4ull * kTilePts) return 4 * kTilePts;
+  if (per >= 2ull * kTilePts) return 2 * kTilePts;
+  return kTilePts;
+}
+
 int set_bin_params(gv_ctx *ctx, const gv_accum_params *prm, BinDev *out)
 {
   GV_REQUIRE(ctx->has_grid, GV_ERR_STATE, "grid not initialised");
@@ -223,6 +243,7 @@ int set_bin_params(gv_ctx *ctx, const gv_accum_params *prm, BinDev *out)
   out->cap = prm->r_max > 0.0 ? 1 : 0;
   out->r_max = prm->r_max;
   out->rmax2 = prm->r_max * prm->r_max;
+  out->inv_res = 1.0 / ctx->g.res;
   return GV_OK;
 }
 
@@ -256,7 +277,9 @@ void fill_point_args_cloud(gv_ctx *ctx, PointArgs &a, const float *x, const floa
   a.n = n;
   a.is_dense = is_dense;
   a.vec_ok = (((uintptr_t)x | (uintptr_t)y | (uintptr_t)z) & 15u) == 0;
-  a.stat_beams = ctx->d_stats;
+  a.tile_pts = tile_points_for(n, ctx->num_sms);
+  a.smem_boxes = 1;
+  a.mask_words = 1;
 }
 
 int fuse_dev_impl(gv_ctx *ctx, const float *d_x, const float *d_y, const float *d_z, size_t n,
@@ -285,11 +308,44 @@ int fuse_dev_impl(gv_ctx *ctx, const float *d_x, const float *d_y, const float *
   a.labels = d_labels;
   a.pix = d_pix;
   a.uv = d_uv;
-  const size_t smem = (size_t)(nboxes > 0 ? nboxes : 1) * sizeof(float4);
+  // per-camera tile masks
+  int max_set = 1, max_tiles = 1;
+  std::vector<int> set_off((size_t)ctx->ncam + 1);
+  for (int c = 0; c < ctx->ncam; ++c) {
+    int ty;
+    mask_geometry(a.cam[c].W, a.cam[c].H, &a.mask_shift[c], &a.mask_tx[c], &ty);
+    if (a.mask_tx[c] * ty > max_tiles) max_tiles = a.mask_tx[c] * ty;
+    const int nb = a.cam[c].box_end - a.cam[c].box_begin;
+    if (nb > max_set) max_set = nb;
+    set_off[c] = a.cam[c].box_begin;
+    GV_REQUIRE(c == 0 || a.cam[c].box_begin == a.cam[c - 1].box_end, GV_ERR_INVALID,
+               "box_cam_offsets must be contiguous");
+  }
+  set_off[ctx->ncam] = a.cam[ctx->ncam - 1].box_end;
+  a.mask_words = (max_set + 63) / 64;
+  a.mask_stride = max_tiles * a.mask_words;
+  a.smem_boxes = nboxes > 0 ? nboxes : 1;
+  unsigned long long *d_masks = nullptr;
+  int *d_set_off = nullptr;
+  GV_TRY(reserve_t(ctx, S_MASKS, (size_t)ctx->ncam * a.mask_stride, &d_masks));
+  GV_TRY(reserve_t(ctx, S_SET_OFF, (size_t)ctx->ncam + 1, &d_set_off));
+  GV_CUDA(cudaMemcpyAsync(d_set_off, set_off.data(), set_off.size() * sizeof(int),
+                          cudaMemcpyHostToDevice, ctx->stream));
+  for (int c = 0; c < ctx->ncam; ++c) {
+    int sh, tx, ty;
+    mask_geometry(a.cam[c].W, a.cam[c].H, &sh, &tx, &ty);
+    k_box_masks<<<1, kThreads, 0, ctx->stream>>>(d_f4, d_set_off + c, sh, tx, ty, a.mask_words,
+                                                 a.mask_stride, d_masks + (size_t)c * a.mask_stride);
+    GV_LAUNCH_CHECK();
+  }
+  GV_CUDA(cudaStreamSynchronize(ctx->stream));  // set_off is a host temporary
+  a.masks = d_masks;
+  const size_t smem = (size_t)a.smem_boxes * sizeof(float4) +
+                      (size_t)ctx->ncam * a.mask_stride * sizeof(unsigned long long);
   if (smem > 48 * 1024)
     GV_CUDA(cudaFuncSetAttribute(k_points<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
-  return launch_points(ctx, true, false, a, blocks_for(n, kTilePts), smem);
+  return launch_points(ctx, true, false, a, blocks_for(n, a.tile_pts), smem);
 }
 
 int accumulate_dev_impl(gv_ctx *ctx, const float *d_x, const float *d_y, const float *d_z, size_t n,
@@ -307,7 +363,7 @@ int accumulate_dev_impl(gv_ctx *ctx, const float *d_x, const float *d_y, const f
   a.cell_out = d_cell;
   a.flags_out = d_flags;
   ctx->ends_dirty = true;
-  return launch_points(ctx, false, true, a, blocks_for(n, kTilePts), 16);
+  return launch_points(ctx, false, true, a, blocks_for(n, a.tile_pts), 32);
 }
 
 int raycast_flush_impl(gv_ctx *ctx, unsigned rank, unsigned world)
@@ -317,7 +373,7 @@ int raycast_flush_impl(gv_ctx *ctx, unsigned rank, unsigned world)
   const unsigned nb = (unsigned)ctx->num_sms * 8u;
   k_ends_compact<<<nb, kThreads, 0, ctx->stream>>>(ctx->d_ends, ctx->ncells, ctx->d_hit,
                                                    ctx->d_miss, ctx->d_list, ctx->d_list_count,
-                                                   rank, world);
+                                                   rank, world, ctx->d_stats);
   GV_LAUNCH_CHECK();
   k_raycast_lines<<<nb, kThreads, 0, ctx->stream>>>(ctx->d_list, ctx->d_list_count, ctx->bin.sx,
                                                     ctx->bin.sy, ctx->g.nx, ctx->d_miss,
@@ -568,7 +624,9 @@ int gv_set_stream(gv_ctx *ctx, void *stream)
 {
   if (!ctx) return GV_ERR_INVALID;
   GV_CUDA(cudaStreamSynchronize(ctx->stream));
-  ctx->stream = stream ? (cudaStream_t)stream : ctx->own_stream;
+  // the handle is used as given: NULL is the legacy default stream (torch's default current
+  // stream), not "reset"; gv_stream() of a fresh context returns its private stream
+  ctx->stream = (cudaStream_t)stream;
   return GV_OK;
 }
 
@@ -1055,7 +1113,8 @@ static int process_batch_impl(gv_ctx *ctx, const float *px, const float *py, con
   GV_TRY(set_bin_params(ctx, prm, &a.bin));
   GV_TRY(note_beams(ctx, n));
 
-  // tile table: one entry per 1024-point tile, tiles never straddle frames
+  // tile table: one entry per CTA tile, tiles never straddle frames
+  const int tile_pts = tile_points_for(n, ctx->num_sms);
   std::vector<unsigned> tile_prefix((size_t)nframes + 1);
   int max_boxes = 1;
   unsigned long long ntiles64 = 0;
@@ -1066,7 +1125,7 @@ static int process_batch_impl(gv_ctx *ctx, const float *px, const float *py, con
     GV_REQUIRE(nb >= 0 && nb <= 32767, GV_ERR_INVALID, "frame %d has %d boxes", f, nb);
     if (nb > max_boxes) max_boxes = nb;
     tile_prefix[f] = (unsigned)ntiles64;
-    ntiles64 += (frame_offsets[f + 1] - frame_offsets[f] + kTilePts - 1) / kTilePts;
+    ntiles64 += (frame_offsets[f + 1] - frame_offsets[f] + tile_pts - 1) / tile_pts;
     GV_REQUIRE(ntiles64 < 2147483647ull, GV_ERR_INVALID, "batch too large");
   }
   tile_prefix[nframes] = (unsigned)ntiles64;
@@ -1075,7 +1134,7 @@ static int process_batch_impl(gv_ctx *ctx, const float *px, const float *py, con
   unsigned long long *d_foff, *d_tstart, *d_tend;
   int *d_boff;
   unsigned *d_tprefix;
-  int2 *d_tbox;
+  int4 *d_tbox;
   GV_TRY(reserve_t(ctx, S_FRAME_OFF, (size_t)nframes + 1, &d_foff));
   GV_TRY(reserve_t(ctx, S_BOX_OFF, (size_t)nframes + 1, &d_boff));
   GV_TRY(reserve_t(ctx, S_TILE_PREFIX, (size_t)nframes + 1, &d_tprefix));
@@ -1107,11 +1166,24 @@ static int process_batch_impl(gv_ctx *ctx, const float *px, const float *py, con
                           cudaMemcpyHostToDevice, ctx->stream));
   GV_CUDA(cudaMemcpyAsync(d_tprefix, tile_prefix.data(), tile_prefix.size() * sizeof(unsigned),
                           cudaMemcpyHostToDevice, ctx->stream));
-  k_build_tiles<<<nframes, 128, 0, ctx->stream>>>(d_foff, d_boff, d_tprefix, nframes, d_tstart,
-                                                 d_tend, d_tbox);
+  k_build_tiles<<<nframes, 128, 0, ctx->stream>>>(d_foff, d_boff, d_tprefix, nframes, tile_pts,
+                                                 d_tstart, d_tend, d_tbox);
   GV_LAUNCH_CHECK();
   float4 *d_f4 = nullptr;
   GV_TRY(upload_boxes(ctx, boxes, nboxes, boxes_on_device, &d_f4));
+  // per-frame image-tile box masks
+  int mty;
+  mask_geometry(ctx->cam[0].W, ctx->cam[0].H, &a.mask_shift[0], &a.mask_tx[0], &mty);
+  a.mask_words = (max_boxes + 63) / 64;
+  a.mask_stride = a.mask_tx[0] * mty * a.mask_words;
+  a.smem_boxes = max_boxes;
+  unsigned long long *d_masks = nullptr;
+  GV_TRY(reserve_t(ctx, S_MASKS, (size_t)nframes * a.mask_stride, &d_masks));
+  k_box_masks<<<nframes, kThreads, 0, ctx->stream>>>(d_f4, d_boff, a.mask_shift[0], a.mask_tx[0],
+                                                    mty, a.mask_words, a.mask_stride, d_masks);
+  GV_LAUNCH_CHECK();
+  a.masks = d_masks;
+  a.tile_pts = tile_pts;
   // host staging below reads foff/tile_prefix only on the host; the async copies above read
   // pageable host vectors, so make sure they are consumed before the vectors die
   GV_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1131,9 +1203,9 @@ static int process_batch_impl(gv_ctx *ctx, const float *px, const float *py, con
   a.tile_end = d_tend;
   a.tile_boxes = d_tbox;
   a.ends = ctx->d_ends;
-  a.stat_beams = ctx->d_stats;
   ctx->ends_dirty = true;
-  const size_t smem = (size_t)max_boxes * sizeof(float4);
+  const size_t smem = (size_t)max_boxes * sizeof(float4) +
+                      (size_t)a.mask_stride * sizeof(unsigned long long);
   if (smem > 48 * 1024)
     GV_CUDA(cudaFuncSetAttribute(k_points<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));

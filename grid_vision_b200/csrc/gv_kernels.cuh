@@ -51,6 +51,7 @@ struct BinDev {
   int occ_mode, use_z_gate;
   float z_min, z_max;
   double r_max, rmax2;
+  double inv_res;  // RN(1/res): certified-quotient fast path in grid_get_index_fast
   int cap;
 };
 
@@ -62,23 +63,30 @@ struct PointArgs {
   // fusion
   int ncam;
   CamDev cam[kMaxCam];
-  const float4 *boxes;  // (x_min, y_min, x_max, y_max) pre-rounded to float, see round_boxes
-  int16_t *labels;      // cam-major planes, stride n (nullable)
-  int32_t *pix;         // nullable
-  float *uv;            // nullable
+  const float4 *boxes;  // (x_min, y_min, x_max, y_max) pre-rounded to float, see k_round_boxes
+  // image-tile prefilter (k_box_masks): per box set (camera, or frame in batch mode) one
+  // bit mask per tile of 2^mask_shift x 2^mask_shift pixels naming the boxes that overlap it
+  const unsigned long long *masks;  // [nsets][mask_stride]
+  int mask_shift[kMaxCam], mask_tx[kMaxCam];
+  int mask_words;   // 64-bit words per tile
+  int mask_stride;  // words per set
+  int smem_boxes;   // float4 slots reserved for boxes in dynamic shared memory
+  int16_t *labels;  // cam-major planes, stride n (nullable)
+  int32_t *pix;     // nullable
+  float *uv;        // nullable
   // batch mode (per-frame box lists, camera 0 only); nframes == 0 -> single cloud
   int nframes;
   unsigned tile0;                        // first tile of this launch (chunked batches)
+  int tile_pts;                          // points per CTA tile (multiple of kTilePts)
   const unsigned long long *tile_start;  // [ntiles] first point of the tile
   const unsigned long long *tile_end;    // [ntiles] end of the tile's frame (exclusive)
-  const int2 *tile_boxes;                // [ntiles] box range of the tile's frame
+  const int4 *tile_boxes;                // [ntiles] (box_begin, box_end, frame, 0)
   // binning
   BinDev bin;
   const int16_t *labels_in;  // labels for GV_OCC_LABELLED when not fusing in the same pass
   unsigned long long *ends;  // per cell: low 32 = beams ending here, high 32 = of which hits
   int32_t *cell_out;         // nullable
   uint8_t *flags_out;        // nullable
-  unsigned long long *stat_beams;
 };
 
 // ----------------------------------------------------------------------------------
@@ -156,6 +164,35 @@ __device__ __forceinline__ bool grid_get_index(const GridGeom &g, double px, dou
   return true;
 }
 
+// Same result as grid_get_index, without the two double divisions in the common case.
+// The contract is index = trunc(-RN(t/res)) with t = (p - half) - pos.  a' = -(t * RN(1/res))
+// differs from -RN(t/res) by at most |a'| * 3.4e-16 (< 1e-6 for any int32 index), so when a'
+// is farther than 1e-6 from an integer both truncate to the same cell; otherwise (a point on
+// a cell boundary to ~1e-6 cells) the exact division decides.  Bit-identical by construction.
+__device__ __forceinline__ int trunc_index(double t, double res, double inv_res)
+{
+  const double a = -__dmul_rn(t, inv_res);
+  const int i = __double2int_rz(a);
+  const double f = __dsub_rn(a, (double)i);
+  if (f > 1e-6 && f < 1.0 - 1e-6) return i;
+  return __double2int_rz(-__ddiv_rn(t, res));
+}
+
+__device__ __forceinline__ bool grid_get_index_fast(const GridGeom &g, double inv_res, double px,
+                                                    double py, int &ix, int &iy)
+{
+  const double qx = -__dsub_rn(__dsub_rn(px, g.pos_x), g.half_x);
+  const double qy = -__dsub_rn(__dsub_rn(py, g.pos_y), g.half_y);
+  if (!(qx >= 0.0 && qy >= 0.0 && qx < g.len_x && qy < g.len_y)) return false;
+  // inside the map rectangle |a| <= size + 1, so the int conversions below are in range
+  const int i = trunc_index(__dsub_rn(__dsub_rn(px, g.half_x), g.pos_x), g.res, inv_res);
+  const int j = trunc_index(__dsub_rn(__dsub_rn(py, g.half_y), g.pos_y), g.res, inv_res);
+  if (!(i >= 0 && j >= 0 && i < g.nx && j < g.ny)) return false;
+  ix = i;
+  iy = j;
+  return true;
+}
+
 // oracle gvo_clip_end: parametric clip in continuous index space, fixed op order.
 __device__ __forceinline__ void clip_end(double oax, double oay, double eax, double eay, int nx,
                                          int ny, int &ex, int &ey)
@@ -209,7 +246,7 @@ __device__ __forceinline__ void bin_point(const BinDev &b, float x, float y, flo
     }
   }
   int ex, ey;
-  if (!grid_get_index(b.g, px, py, ex, ey)) {
+  if (!grid_get_index_fast(b.g, b.inv_res, px, py, ex, ey)) {
     const double eax = index_coord(px, b.g.half_x, b.g.pos_x, b.g.res);
     const double eay = index_coord(py, b.g.half_y, b.g.pos_y, b.g.res);
     clip_end(b.oax, b.oay, eax, eay, b.g.nx, b.g.ny, ex, ey);
@@ -224,181 +261,212 @@ __device__ __forceinline__ void bin_point(const BinDev &b, float x, float y, flo
 
 // ----------------------------------------------------------------------------------
 // K1/K2: fused transform + project + box-label (+ base transform + cell + bin).
-// One CTA = one tile of 1024 consecutive points of one frame; one thread = 4 consecutive
-// points (three 128-bit loads when aligned).  The frame's detection boxes are staged in
-// shared memory and read with broadcast LDS.128.
+// One CTA = one tile of tile_pts consecutive points of one frame, processed 1024 at a time;
+// one thread = 4 consecutive points per pass (three 128-bit loads when aligned).  The frame's
+// detection boxes and its image-tile box masks are staged once per CTA in shared memory.
+// No barrier after the staging one: warps retire independently (projection and box tests
+// make per-warp work very uneven).
 // ----------------------------------------------------------------------------------
 template <bool FUSE, bool BIN>
 __global__ void __launch_bounds__(kThreads) k_points(const __grid_constant__ PointArgs a)
 {
-  extern __shared__ float4 s_box[];
-  __shared__ unsigned s_beams[kThreads / 32];
+  extern __shared__ float4 s_dyn[];
+  float4 *s_box = s_dyn;
+  const unsigned long long *s_mask = reinterpret_cast<const unsigned long long *>(s_dyn + a.smem_boxes);
 
   unsigned long long start, end;
-  int bb = 0, be = 0;
+  int bb = 0, be = 0, set0 = 0;
   const unsigned tile = blockIdx.x + a.tile0;
   if (a.nframes > 0) {
     start = a.tile_start[tile];
     end = a.tile_end[tile];
-    const int2 br = a.tile_boxes[tile];
+    const int4 br = a.tile_boxes[tile];
     bb = br.x;
     be = br.y;
+    set0 = br.z;
   } else {
-    start = (unsigned long long)tile * kTilePts;
+    start = (unsigned long long)tile * (unsigned)a.tile_pts;
     end = a.n;
   }
-  if (end > start + kTilePts) end = start + kTilePts;
+  if (end > start + (unsigned)a.tile_pts) end = start + (unsigned)a.tile_pts;
 
   if (FUSE) {
-    // stage boxes: batch mode -> this frame's list; otherwise every camera's list
+    // stage boxes + tile masks: batch mode -> this frame's set; otherwise every camera's set
     const int b0 = a.nframes > 0 ? bb : 0;
     const int b1 = a.nframes > 0 ? be : a.cam[a.ncam - 1].box_end;
     for (int i = b0 + threadIdx.x; i < b1; i += kThreads) s_box[i - b0] = a.boxes[i];
+    const int nm = (a.nframes > 0 ? 1 : a.ncam) * a.mask_stride;
+    const unsigned long long *gm = a.masks + (size_t)set0 * a.mask_stride;
+    unsigned long long *sm = const_cast<unsigned long long *>(s_mask);
+    for (int i = threadIdx.x; i < nm; i += kThreads) sm[i] = gm[i];
     __syncthreads();
   }
 
-  const unsigned long long i0 = start + (unsigned long long)threadIdx.x * kPtsPerThread;
-  float px[4], py[4], pz[4];
-  bool live[4];
-  if (a.vec_ok && ((i0 & 3ull) == 0) && i0 + 4 <= end) {
-    const float4 vx = __ldg(reinterpret_cast<const float4 *>(a.x + i0));
-    const float4 vy = __ldg(reinterpret_cast<const float4 *>(a.y + i0));
-    const float4 vz = __ldg(reinterpret_cast<const float4 *>(a.z + i0));
-    px[0] = vx.x; px[1] = vx.y; px[2] = vx.z; px[3] = vx.w;
-    py[0] = vy.x; py[1] = vy.y; py[2] = vy.z; py[3] = vy.w;
-    pz[0] = vz.x; pz[1] = vz.y; pz[2] = vz.z; pz[3] = vz.w;
-    live[0] = live[1] = live[2] = live[3] = true;
-  } else {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      live[j] = i0 + j < end;
-      px[j] = live[j] ? __ldg(a.x + i0 + j) : 0.0f;
-      py[j] = live[j] ? __ldg(a.y + i0 + j) : 0.0f;
-      pz[j] = live[j] ? __ldg(a.z + i0 + j) : 0.0f;
-    }
-  }
-
-  int lab0[4] = {-1, -1, -1, -1};
-
-  if (FUSE) {
-    for (int c = 0; c < a.ncam; ++c) {
-      const CamDev &cam = a.cam[c];
-      float u[4], v[4];
-      int lab[4], pix[4];
-      unsigned pending = 0;
+  for (unsigned long long base = start; base < end; base += kTilePts) {
+    const unsigned long long i0 = base + (unsigned long long)threadIdx.x * kPtsPerThread;
+    if (i0 >= end) break;
+    float px[4], py[4], pz[4];
+    bool live[4];
+    if (a.vec_ok && ((i0 & 3ull) == 0) && i0 + 4 <= end) {
+      const float4 vx = __ldg(reinterpret_cast<const float4 *>(a.x + i0));
+      const float4 vy = __ldg(reinterpret_cast<const float4 *>(a.y + i0));
+      const float4 vz = __ldg(reinterpret_cast<const float4 *>(a.z + i0));
+      px[0] = vx.x; px[1] = vx.y; px[2] = vx.z; px[3] = vx.w;
+      py[0] = vy.x; py[1] = vy.y; py[2] = vy.z; py[3] = vy.w;
+      pz[0] = vz.x; pz[1] = vz.y; pz[2] = vz.z; pz[3] = vz.w;
+      live[0] = live[1] = live[2] = live[3] = true;
+    } else {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        lab[j] = -1;
-        pix[j] = -1;
-        u[j] = v[j] = __int_as_float(0x7fc00000);
-        if (!live[j]) continue;
-        float X = px[j], Y = py[j], Z = pz[j];
-        // R1 (pcl::transformPointCloud: non-finite points pass through when !is_dense)
-        if (cam.has_T && (a.is_dense || finite3(X, Y, Z))) se3(cam.T, px[j], py[j], pz[j], X, Y, Z);
-        // ref: src/cloud_detections.cpp:264
-        if (!finite3(X, Y, Z) || Z <= 0.001f) continue;
-        project_point(cam, X, Y, Z, u[j], v[j]);
-        // ref: :276  (float vs int -> the int is converted to float)
-        if (u[j] < 0.0f || u[j] >= cam.Wf || v[j] < 0.0f || v[j] >= cam.Hf) continue;
-        pix[j] = (int)v[j] * cam.W + (int)u[j];
-        pending |= 1u << j;
+        live[j] = i0 + j < end;
+        px[j] = live[j] ? __ldg(a.x + i0 + j) : 0.0f;
+        py[j] = live[j] ? __ldg(a.y + i0 + j) : 0.0f;
+        pz[j] = live[j] ? __ldg(a.z + i0 + j) : 0.0f;
       }
-      // ref: :280-288 first box in list order wins, inclusive bounds.  The double bounds
-      // were rounded to float on the host (ceil for mins, floor for maxes) so these float
-      // compares decide exactly like the reference's float-vs-double compares.
-      const int b0 = a.nframes > 0 ? bb : cam.box_begin;
-      const int b1 = a.nframes > 0 ? be : cam.box_end;
-      const int sb = a.nframes > 0 ? bb : 0;
-      for (int b = b0; b < b1 && pending; ++b) {
-        const float4 B = s_box[b - sb];
+    }
+
+    int lab0[4] = {-1, -1, -1, -1};
+
+    if (FUSE) {
+      for (int c = 0; c < a.ncam; ++c) {
+        const CamDev &cam = a.cam[c];
+        // box list + mask set of this camera (single cloud) or of this tile's frame (batch)
+        const int b0 = a.nframes > 0 ? 0 : cam.box_begin;               // offset inside s_box
+        const int nb = a.nframes > 0 ? be - bb : cam.box_end - cam.box_begin;
+        const unsigned long long *mset = s_mask + (a.nframes > 0 ? 0 : c * a.mask_stride);
+        const int shift = a.mask_shift[c], mtx = a.mask_tx[c];
+        float u[4], v[4];
+        int lab[4], pix[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          if ((pending >> j) & 1u) {
-            if (u[j] >= B.x && u[j] <= B.z && v[j] >= B.y && v[j] <= B.w) {
-              lab[j] = b - b0;
-              pending &= ~(1u << j);
+          lab[j] = -1;
+          pix[j] = -1;
+          u[j] = v[j] = __int_as_float(0x7fc00000);
+          if (!live[j]) continue;
+          float X = px[j], Y = py[j], Z = pz[j];
+          // R1 (pcl::transformPointCloud: non-finite points pass through when !is_dense)
+          if (cam.has_T && (a.is_dense || finite3(X, Y, Z))) se3(cam.T, px[j], py[j], pz[j], X, Y, Z);
+          // ref: src/cloud_detections.cpp:264
+          if (!finite3(X, Y, Z) || Z <= 0.001f) continue;
+          project_point(cam, X, Y, Z, u[j], v[j]);
+          // ref: :276  (float vs int -> the int is converted to float)
+          if (u[j] < 0.0f || u[j] >= cam.Wf || v[j] < 0.0f || v[j] >= cam.Hf) continue;
+          const int iu = (int)u[j], iv = (int)v[j];
+          pix[j] = iv * cam.W + iu;
+          // ref: :280-288 first box in list order wins, inclusive bounds.  Only boxes whose
+          // rectangle overlaps this point's image tile can contain it (k_box_masks); they
+          // are visited in ascending index order, so the first hit is the reference's.
+          // The double bounds were rounded to float on the device (k_round_boxes) so these
+          // float compares decide exactly like the reference's float-vs-double compares.
+          if (nb > 0) {
+            const unsigned long long *mrow = mset + ((iv >> shift) * mtx + (iu >> shift)) * a.mask_words;
+            for (int w = 0; w < a.mask_words && lab[j] < 0; ++w) {
+              unsigned long long m = mrow[w];
+              while (m) {
+                const int b = w * 64 + __ffsll((long long)m) - 1;
+                m &= m - 1;
+                const float4 B = s_box[b0 + b];
+                if (u[j] >= B.x && u[j] <= B.z && v[j] >= B.y && v[j] <= B.w) {
+                  lab[j] = b;
+                  break;
+                }
+              }
             }
           }
         }
-      }
-      if (c == 0) {
+        if (c == 0) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) lab0[j] = lab[j];
-      }
-      const unsigned long long plane = (unsigned long long)c * a.n;
-      if (a.labels) {
-        int16_t *lp = a.labels + plane + i0;
-        if (live[3] && ((reinterpret_cast<uintptr_t>(lp) & 7u) == 0)) {
-          short4 s;
-          s.x = (short)lab[0]; s.y = (short)lab[1]; s.z = (short)lab[2]; s.w = (short)lab[3];
-          *reinterpret_cast<short4 *>(lp) = s;
-        } else {
+          for (int j = 0; j < 4; ++j) lab0[j] = lab[j];
+        }
+        const unsigned long long plane = (unsigned long long)c * a.n;
+        if (a.labels) {
+          int16_t *lp = a.labels + plane + i0;
+          if (live[3] && ((reinterpret_cast<uintptr_t>(lp) & 7u) == 0)) {
+            short4 sv;
+            sv.x = (short)lab[0]; sv.y = (short)lab[1]; sv.z = (short)lab[2]; sv.w = (short)lab[3];
+            *reinterpret_cast<short4 *>(lp) = sv;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (live[j]) lp[j] = (int16_t)lab[j];
+          }
+        }
+        if (a.pix) {
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            if (live[j]) lp[j] = (int16_t)lab[j];
+            if (live[j]) a.pix[plane + i0 + j] = pix[j];
+        }
+        if (a.uv) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (live[j]) {
+              a.uv[2 * plane + i0 + j] = u[j];
+              a.uv[2 * plane + a.n + i0 + j] = v[j];
+            }
         }
       }
-      if (a.pix) {
+    }
+
+    if (BIN) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (live[j]) a.pix[plane + i0 + j] = pix[j];
-      }
-      if (a.uv) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (live[j]) {
-            a.uv[2 * plane + i0 + j] = u[j];
-            a.uv[2 * plane + a.n + i0 + j] = v[j];
-          }
+      for (int j = 0; j < 4; ++j) {
+        if (!live[j]) continue;
+        int label = lab0[j];
+        if (!FUSE && a.labels_in) label = a.labels_in[i0 + j];
+        int cell;
+        unsigned flags;
+        bin_point(a.bin, px[j], py[j], pz[j], label, cell, flags);
+        // one 64-bit RED per beam: low word counts beams ending in the cell, high word hits
+        if (cell >= 0) atomicAdd(a.ends + cell, (flags & 2u) ? 0x100000001ull : 1ull);
+        if (a.cell_out) a.cell_out[i0 + j] = cell;
+        if (a.flags_out) a.flags_out[i0 + j] = (uint8_t)flags;
       }
     }
   }
+}
 
-  if (BIN) {
-    unsigned nbeams = 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (!live[j]) continue;
-      int label = lab0[j];
-      if (!FUSE && a.labels_in) label = a.labels_in[i0 + j];
-      int cell;
-      unsigned flags;
-      bin_point(a.bin, px[j], py[j], pz[j], label, cell, flags);
-      if (cell >= 0) {
-        // one 64-bit RED per beam: low word counts beams ending in the cell, high word hits
-        atomicAdd(a.ends + cell, (flags & 2u) ? 0x100000001ull : 1ull);
-        ++nbeams;
-      }
-      if (a.cell_out) a.cell_out[i0 + j] = cell;
-      if (a.flags_out) a.flags_out[i0 + j] = (uint8_t)flags;
+// Image-tile prefilter for the box test.  One CTA per box set (a camera, or a frame in batch
+// mode); bit b of masks[set][tile*words + b/64] is set iff box b (index local to the set)
+// overlaps the tile's pixel square [tx*S, (tx+1)*S) x [ty*S, (ty+1)*S), S = 2^shift.
+// A point with float pixel (u,v) lies in tile ((int)u >> shift, (int)v >> shift), and a box
+// contains it only if x_min <= u <= x_max, so boxes outside the mask can never match; the
+// test is conservative, never lossy.  NaN bounds compare false everywhere -> bit clear.
+__global__ void __launch_bounds__(kThreads) k_box_masks(const float4 *__restrict__ boxes,
+                                                        const int *__restrict__ set_offsets,
+                                                        int shift, int tiles_x, int tiles_y,
+                                                        int words, int stride,
+                                                        unsigned long long *__restrict__ masks)
+{
+  const int set = blockIdx.x;
+  const int b0 = set_offsets[set], b1 = set_offsets[set + 1];
+  const float S = (float)(1 << shift);
+  for (int t = threadIdx.x; t < tiles_x * tiles_y * words; t += kThreads) {
+    const int w = t % words, tile = t / words;
+    const float x0 = (float)(tile % tiles_x) * S, y0 = (float)(tile / tiles_x) * S;
+    unsigned long long m = 0ull;
+    const int bw0 = b0 + w * 64;
+    const int bw1 = bw0 + 64 < b1 ? bw0 + 64 : b1;
+    for (int b = bw0; b < bw1; ++b) {
+      const float4 B = boxes[b];
+      if (B.z >= x0 && B.x < x0 + S && B.w >= y0 && B.y < y0 + S) m |= 1ull << (b - bw0);
     }
-    // per-CTA beam count -> one atomic
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) nbeams += __shfl_xor_sync(0xffffffffu, nbeams, o);
-    if ((threadIdx.x & 31) == 0) s_beams[threadIdx.x >> 5] = nbeams;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned t = 0;
-#pragma unroll
-      for (int w = 0; w < kThreads / 32; ++w) t += s_beams[w];
-      if (t) atomicAdd(a.stat_beams, (unsigned long long)t);
-    }
+    masks[(size_t)set * stride + t] = m;
   }
 }
 
 // per-frame tile table for batch mode: one CTA per frame
 __global__ void k_build_tiles(const unsigned long long *frame_offsets, const int *box_frame_offsets,
                               const unsigned *tile_prefix, int nframes,
-                              unsigned long long *tile_start, unsigned long long *tile_end,
-                              int2 *tile_boxes)
+                              int tile_pts, unsigned long long *tile_start,
+                              unsigned long long *tile_end, int4 *tile_boxes)
 {
   const int f = blockIdx.x;
   if (f >= nframes) return;
   const unsigned long long s = frame_offsets[f], e = frame_offsets[f + 1];
   const unsigned t0 = tile_prefix[f], t1 = tile_prefix[f + 1];
-  const int2 br = make_int2(box_frame_offsets[f], box_frame_offsets[f + 1]);
+  const int4 br = make_int4(box_frame_offsets[f], box_frame_offsets[f + 1], f, 0);
   for (unsigned t = t0 + threadIdx.x; t < t1; t += blockDim.x) {
-    tile_start[t] = s + (unsigned long long)(t - t0) * kTilePts;
+    tile_start[t] = s + (unsigned long long)(t - t0) * (unsigned)tile_pts;
     tile_end[t] = e;
     tile_boxes[t] = br;
   }
@@ -607,9 +675,11 @@ __global__ void __launch_bounds__(kThreads) k_ends_compact(unsigned long long *_
                                                            int32_t *__restrict__ miss,
                                                            uint2 *__restrict__ list,
                                                            unsigned *__restrict__ list_count,
-                                                           unsigned rank, unsigned world)
+                                                           unsigned rank, unsigned world,
+                                                           unsigned long long *__restrict__ stat_beams)
 {
   const unsigned lane = threadIdx.x & 31;
+  unsigned long long beams = 0;
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
   // all lanes of a warp iterate together (bound rounded up to a warp multiple)
   const unsigned long long nround = (ncells + 31ull) & ~31ull;
@@ -617,6 +687,7 @@ __global__ void __launch_bounds__(kThreads) k_ends_compact(unsigned long long *_
        i += stride) {
     unsigned long long e = i < ncells ? ends[i] : 0ull;
     if (e != 0ull) ends[i] = 0ull;
+    if (world == 1u || (unsigned)(i % world) == rank) beams += e & 0xffffffffull;
     // multi-GPU (gv_grid_finalize_multi): every rank holds the all-reduced plane and owns
     // the end cells with lin % world == rank; ownership by CELL, not by list position,
     // because the append order below differs from rank to rank.
@@ -634,6 +705,9 @@ __global__ void __launch_bounds__(kThreads) k_ends_compact(unsigned long long *_
       if (total - hits) miss[i] += (int32_t)(total - hits);
     }
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) beams += __shfl_xor_sync(0xffffffffu, beams, o);
+  if (lane == 0 && beams) atomicAdd(stat_beams, beams);
 }
 
 // grid_map LineIterator restatement (oracle gvo_line_init / gvo_line_step)

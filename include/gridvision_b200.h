@@ -15,8 +15,9 @@
  *    rclcpp::spin executor, ref: src/grid_vision_node.cpp:533-540); use one per thread/GPU.
  *  - functions without a suffix take HOST pointers, copy in/out themselves and are
  *    synchronous on return (drop-in for the reference's blocking calls);
- *    functions ending in _dev take DEVICE pointers and are asynchronous on the context
- *    stream (gv_stream / gv_set_stream).
+ *    functions ending in _dev take DEVICE pointers for the bulk arrays (points, labels and
+ *    gv_box records; per-frame offset tables stay host arrays) and are asynchronous on the
+ *    context stream (gv_stream / gv_set_stream).
  *  - point clouds are SoA float planes (x[], y[], z[]); the reference's
  *    pcl::PointCloud<pcl::PointXYZI> 32-byte AoS records are accepted by the *_aos32 entry
  *    points and de-interleaved on the device.
@@ -103,7 +104,9 @@ GV_API void gv_destroy(gv_ctx *ctx);
 GV_API const char *gv_last_error(const gv_ctx *ctx);
 GV_API int gv_synchronize(gv_ctx *ctx);
 GV_API void *gv_stream(gv_ctx *ctx);               /* cudaStream_t */
-GV_API int gv_set_stream(gv_ctx *ctx, void *stream); /* e.g. the caller's current stream */
+/* launch on the caller's stream from now on; the handle is used as given (NULL = the legacy
+ * default stream).  A fresh context owns a private non-blocking stream. */
+GV_API int gv_set_stream(gv_ctx *ctx, void *stream);
 GV_API int gv_get_stats(gv_ctx *ctx, gv_stats *out);
 
 /* ------------------------------------------------------------ fusion (R1-R5) --- */
@@ -130,7 +133,7 @@ GV_API int gv_fuse_aos32(gv_ctx *ctx, const gv_point_xyzi *pts, size_t n, int is
                          const gv_box *boxes, int nboxes, const int32_t *box_cam_offsets,
                          int16_t *labels_out, int32_t *pix_out, float *uv_out);
 GV_API int gv_fuse_dev(gv_ctx *ctx, const float *d_x, const float *d_y, const float *d_z, size_t n,
-                       int is_dense, const gv_box *boxes, int nboxes,
+                       int is_dense, const gv_box *d_boxes, int nboxes,
                        const int32_t *box_cam_offsets, int16_t *d_labels_out, int32_t *d_pix_out,
                        float *d_uv_out);
 
@@ -217,7 +220,7 @@ GV_API int gv_process_batch(gv_ctx *ctx, const float *x, const float *y, const f
                             const int32_t *box_frame_offsets, const gv_accum_params *prm,
                             int16_t *labels_out);
 GV_API int gv_process_batch_dev(gv_ctx *ctx, const float *d_x, const float *d_y, const float *d_z,
-                                const uint64_t *frame_offsets, int nframes, const gv_box *boxes,
+                                const uint64_t *frame_offsets, int nframes, const gv_box *d_boxes,
                                 const int32_t *box_frame_offsets, const gv_accum_params *prm,
                                 int16_t *d_labels_out);
 

@@ -123,6 +123,22 @@ def test_fuse_degenerate_boxes(ctx):
     assert set(np.unique(elab)) >= {-1, 2, 3, 4} and 0 not in elab and 1 not in elab
 
 
+def test_fuse_many_boxes_multiword_masks(ctx):
+    """150 boxes in one camera: the image-tile prefilter needs three 64-bit words per tile."""
+    wl = small(synth.C1, rings=64, azimuth=2048)
+    xyz = scan(wl)
+    boxes = synth.make_boxes(wl, n=150)
+    rng = np.random.default_rng(3)
+    boxes = boxes[rng.permutation(150)]          # overlapping boxes in arbitrary list order
+    boxes["x_max"][::7] += 0.37                  # non-integer, non-float-exact bounds too
+    boxes["y_min"][::5] -= 0.11
+    Ts = set_camera(ctx, wl)
+    lab, pix, uv = ctx.fuse(*xyz, boxes)
+    elab, epix, eu, ev = oracle_fuse(wl, xyz, boxes, Ts[0])
+    assert np.array_equal(lab[0], elab) and np.array_equal(pix[0], epix)
+    assert len(np.unique(elab)) > 30 and elab.max() >= 128  # all three mask words in play
+
+
 def test_fuse_aos32_layout(ctx):
     wl = small(synth.C1, rings=32, azimuth=1024)
     xyz = scan(wl)
@@ -217,7 +233,7 @@ def test_update_map_decay_R7(ctx):
         lo, oc = ctx.grid_download()
         assert_bits_equal(lo, g.log_odds, f"log_odds after {k + 1} updates")
         assert rel_close(oc, g.occupancy, OCC_RTOL)
-    assert np.all(lo == np.float32(-2.0))
+    assert lo.min() == np.float32(-2.0) and lo.max() < np.float32(3.6)
 
 
 def test_update_map_poses_R8(ctx):
