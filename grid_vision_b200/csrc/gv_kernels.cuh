@@ -261,8 +261,8 @@ __device__ __forceinline__ void bin_point(const BinDev &b, float x, float y, flo
 
 // ----------------------------------------------------------------------------------
 // K1/K2: fused transform + project + box-label (+ base transform + cell + bin).
-// One CTA = one tile of tile_pts consecutive points of one frame, processed 1024 at a time;
-// one thread = 4 consecutive points per pass (three 128-bit loads when aligned).  The frame's
+// One CTA = one tile of tile_pts consecutive points of one frame, 256 points per pass (one per
+// thread, coalesced 128-byte rows per warp, next pass prefetched).  The frame's
 // detection boxes and its image-tile box masks are staged once per CTA in shared memory.
 // No barrier after the staging one: warps retire independently (projection and box tests
 // make per-warp work very uneven).
@@ -302,126 +302,95 @@ __global__ void __launch_bounds__(kThreads) k_points(const __grid_constant__ Poi
     __syncthreads();
   }
 
-  for (unsigned long long base = start; base < end; base += kTilePts) {
-    const unsigned long long i0 = base + (unsigned long long)threadIdx.x * kPtsPerThread;
-    if (i0 >= end) break;
-    float px[4], py[4], pz[4];
-    bool live[4];
-    if (a.vec_ok && ((i0 & 3ull) == 0) && i0 + 4 <= end) {
-      const float4 vx = __ldg(reinterpret_cast<const float4 *>(a.x + i0));
-      const float4 vy = __ldg(reinterpret_cast<const float4 *>(a.y + i0));
-      const float4 vz = __ldg(reinterpret_cast<const float4 *>(a.z + i0));
-      px[0] = vx.x; px[1] = vx.y; px[2] = vx.z; px[3] = vx.w;
-      py[0] = vy.x; py[1] = vy.y; py[2] = vy.z; py[3] = vy.w;
-      pz[0] = vz.x; pz[1] = vz.y; pz[2] = vz.z; pz[3] = vz.w;
-      live[0] = live[1] = live[2] = live[3] = true;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        live[j] = i0 + j < end;
-        px[j] = live[j] ? __ldg(a.x + i0 + j) : 0.0f;
-        py[j] = live[j] ? __ldg(a.y + i0 + j) : 0.0f;
-        pz[j] = live[j] ? __ldg(a.z + i0 + j) : 0.0f;
-      }
+  // One point per thread per pass, next pass prefetched.  (A 4-points-per-thread version with
+  // 128-bit loads ran out of instruction cache: 3.4k SASS instructions, 41% no-instruction
+  // stalls in ncu; the path is issue-bound, not load-bound, so scalar coalesced loads win.)
+  unsigned long long i = start + threadIdx.x;
+  float nx = 0.0f, ny = 0.0f, nz = 0.0f;
+  if (i < end) {
+    nx = __ldg(a.x + i);
+    ny = __ldg(a.y + i);
+    nz = __ldg(a.z + i);
+  }
+#pragma unroll 1
+  while (i < end) {
+    const float px = nx, py = ny, pz = nz;
+    const unsigned long long inext = i + kThreads;
+    if (inext < end) {
+      nx = __ldg(a.x + inext);
+      ny = __ldg(a.y + inext);
+      nz = __ldg(a.z + inext);
     }
-
-    int lab0[4] = {-1, -1, -1, -1};
+    int lab0 = -1;
 
     if (FUSE) {
+#pragma unroll 1
       for (int c = 0; c < a.ncam; ++c) {
         const CamDev &cam = a.cam[c];
         // box list + mask set of this camera (single cloud) or of this tile's frame (batch)
-        const int b0 = a.nframes > 0 ? 0 : cam.box_begin;               // offset inside s_box
+        const int b0 = a.nframes > 0 ? 0 : cam.box_begin;  // offset inside s_box
         const int nb = a.nframes > 0 ? be - bb : cam.box_end - cam.box_begin;
         const unsigned long long *mset = s_mask + (a.nframes > 0 ? 0 : c * a.mask_stride);
-        const int shift = a.mask_shift[c], mtx = a.mask_tx[c];
-        float u[4], v[4];
-        int lab[4], pix[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          lab[j] = -1;
-          pix[j] = -1;
-          u[j] = v[j] = __int_as_float(0x7fc00000);
-          if (!live[j]) continue;
-          float X = px[j], Y = py[j], Z = pz[j];
-          // R1 (pcl::transformPointCloud: non-finite points pass through when !is_dense)
-          if (cam.has_T && (a.is_dense || finite3(X, Y, Z))) se3(cam.T, px[j], py[j], pz[j], X, Y, Z);
-          // ref: src/cloud_detections.cpp:264
-          if (!finite3(X, Y, Z) || Z <= 0.001f) continue;
-          project_point(cam, X, Y, Z, u[j], v[j]);
+        int lab = -1, pix = -1;
+        float u = __int_as_float(0x7fc00000), v = u;
+        float X = px, Y = py, Z = pz;
+        // R1 (pcl::transformPointCloud: non-finite points pass through when !is_dense)
+        if (cam.has_T && (a.is_dense || finite3(X, Y, Z))) se3(cam.T, px, py, pz, X, Y, Z);
+        // ref: src/cloud_detections.cpp:264
+        if (finite3(X, Y, Z) && !(Z <= 0.001f)) {
+          project_point(cam, X, Y, Z, u, v);
           // ref: :276  (float vs int -> the int is converted to float)
-          if (u[j] < 0.0f || u[j] >= cam.Wf || v[j] < 0.0f || v[j] >= cam.Hf) continue;
-          const int iu = (int)u[j], iv = (int)v[j];
-          pix[j] = iv * cam.W + iu;
-          // ref: :280-288 first box in list order wins, inclusive bounds.  Only boxes whose
-          // rectangle overlaps this point's image tile can contain it (k_box_masks); they
-          // are visited in ascending index order, so the first hit is the reference's.
-          // The double bounds were rounded to float on the device (k_round_boxes) so these
-          // float compares decide exactly like the reference's float-vs-double compares.
-          if (nb > 0) {
-            const unsigned long long *mrow = mset + ((iv >> shift) * mtx + (iu >> shift)) * a.mask_words;
-            for (int w = 0; w < a.mask_words && lab[j] < 0; ++w) {
-              unsigned long long m = mrow[w];
-              while (m) {
-                const int b = w * 64 + __ffsll((long long)m) - 1;
-                m &= m - 1;
-                const float4 B = s_box[b0 + b];
-                if (u[j] >= B.x && u[j] <= B.z && v[j] >= B.y && v[j] <= B.w) {
-                  lab[j] = b;
-                  break;
+          if (!(u < 0.0f || u >= cam.Wf || v < 0.0f || v >= cam.Hf)) {
+            const int iu = (int)u, iv = (int)v;
+            pix = iv * cam.W + iu;
+            // ref: :280-288 first box in list order wins, inclusive bounds.  Only boxes whose
+            // rectangle overlaps this point's image tile can contain it (k_box_masks); they
+            // are visited in ascending index order, so the first hit is the reference's.
+            // The double bounds were rounded to float on the device (k_round_boxes) so these
+            // float compares decide exactly like the reference's float-vs-double compares.
+            if (nb > 0) {
+              const int shift = a.mask_shift[c];
+              const unsigned long long *mrow =
+                mset + ((iv >> shift) * a.mask_tx[c] + (iu >> shift)) * a.mask_words;
+#pragma unroll 1
+              for (int w = 0; w < a.mask_words && lab < 0; ++w) {
+                unsigned long long m = mrow[w];
+                while (m) {
+                  const int b = w * 64 + __ffsll((long long)m) - 1;
+                  m &= m - 1;
+                  const float4 B = s_box[b0 + b];
+                  if (u >= B.x && u <= B.z && v >= B.y && v <= B.w) {
+                    lab = b;
+                    break;
+                  }
                 }
               }
             }
           }
         }
-        if (c == 0) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) lab0[j] = lab[j];
-        }
+        if (c == 0) lab0 = lab;
         const unsigned long long plane = (unsigned long long)c * a.n;
-        if (a.labels) {
-          int16_t *lp = a.labels + plane + i0;
-          if (live[3] && ((reinterpret_cast<uintptr_t>(lp) & 7u) == 0)) {
-            short4 sv;
-            sv.x = (short)lab[0]; sv.y = (short)lab[1]; sv.z = (short)lab[2]; sv.w = (short)lab[3];
-            *reinterpret_cast<short4 *>(lp) = sv;
-          } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (live[j]) lp[j] = (int16_t)lab[j];
-          }
-        }
-        if (a.pix) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (live[j]) a.pix[plane + i0 + j] = pix[j];
-        }
+        if (a.labels) a.labels[plane + i] = (int16_t)lab;
+        if (a.pix) a.pix[plane + i] = pix;
         if (a.uv) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (live[j]) {
-              a.uv[2 * plane + i0 + j] = u[j];
-              a.uv[2 * plane + a.n + i0 + j] = v[j];
-            }
+          a.uv[2 * plane + i] = u;
+          a.uv[2 * plane + a.n + i] = v;
         }
       }
     }
 
     if (BIN) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (!live[j]) continue;
-        int label = lab0[j];
-        if (!FUSE && a.labels_in) label = a.labels_in[i0 + j];
-        int cell;
-        unsigned flags;
-        bin_point(a.bin, px[j], py[j], pz[j], label, cell, flags);
-        // one 64-bit RED per beam: low word counts beams ending in the cell, high word hits
-        if (cell >= 0) atomicAdd(a.ends + cell, (flags & 2u) ? 0x100000001ull : 1ull);
-        if (a.cell_out) a.cell_out[i0 + j] = cell;
-        if (a.flags_out) a.flags_out[i0 + j] = (uint8_t)flags;
-      }
+      int label = lab0;
+      if (!FUSE && a.labels_in) label = a.labels_in[i];
+      int cell;
+      unsigned flags;
+      bin_point(a.bin, px, py, pz, label, cell, flags);
+      // one 64-bit RED per beam: low word counts beams ending in the cell, high word hits
+      if (cell >= 0) atomicAdd(a.ends + cell, (flags & 2u) ? 0x100000001ull : 1ull);
+      if (a.cell_out) a.cell_out[i] = cell;
+      if (a.flags_out) a.flags_out[i] = (uint8_t)flags;
     }
+    i = inext;
   }
 }
 
