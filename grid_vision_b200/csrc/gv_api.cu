@@ -244,6 +244,7 @@ int set_bin_params(gv_ctx *ctx, const gv_accum_params *prm, BinDev *out)
   out->r_max = prm->r_max;
   out->rmax2 = prm->r_max * prm->r_max;
   out->inv_res = 1.0 / ctx->g.res;
+  out->r_maxf = (float)prm->r_max;
   return GV_OK;
 }
 
@@ -260,9 +261,10 @@ int note_beams(gv_ctx *ctx, unsigned long long n)
 int launch_points(gv_ctx *ctx, bool fuse, bool bin, PointArgs &a, unsigned ntiles, size_t smem)
 {
   if (ntiles == 0) return GV_OK;
-  if (fuse && bin) k_points<true, true><<<ntiles, kThreads, smem, ctx->stream>>>(a);
-  else if (fuse) k_points<true, false><<<ntiles, kThreads, smem, ctx->stream>>>(a);
-  else k_points<false, true><<<ntiles, kThreads, smem, ctx->stream>>>(a);
+  if (fuse && bin) k_points<true, true, false><<<ntiles, kThreads, smem, ctx->stream>>>(a);
+  else if (fuse && a.ncam > 1) k_points<true, false, true><<<ntiles, kThreads, smem, ctx->stream>>>(a);
+  else if (fuse) k_points<true, false, false><<<ntiles, kThreads, smem, ctx->stream>>>(a);
+  else k_points<false, true, false><<<ntiles, kThreads, smem, ctx->stream>>>(a);
   GV_LAUNCH_CHECK();
   return GV_OK;
 }
@@ -342,9 +344,12 @@ int fuse_dev_impl(gv_ctx *ctx, const float *d_x, const float *d_y, const float *
   a.masks = d_masks;
   const size_t smem = (size_t)a.smem_boxes * sizeof(float4) +
                       (size_t)ctx->ncam * a.mask_stride * sizeof(unsigned long long);
-  if (smem > 48 * 1024)
-    GV_CUDA(cudaFuncSetAttribute(k_points<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem));
+  if (smem > 48 * 1024) {
+    GV_CUDA(cudaFuncSetAttribute(k_points<true, false, false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GV_CUDA(cudaFuncSetAttribute(k_points<true, false, true>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
   return launch_points(ctx, true, false, a, blocks_for(n, a.tile_pts), smem);
 }
 
@@ -1207,8 +1212,8 @@ static int process_batch_impl(gv_ctx *ctx, const float *px, const float *py, con
   const size_t smem = (size_t)max_boxes * sizeof(float4) +
                       (size_t)a.mask_stride * sizeof(unsigned long long);
   if (smem > 48 * 1024)
-    GV_CUDA(cudaFuncSetAttribute(k_points<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem));
+    GV_CUDA(cudaFuncSetAttribute(k_points<true, true, false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
   if (points_on_device) {
     a.tile0 = 0;

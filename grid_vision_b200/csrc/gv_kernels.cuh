@@ -52,6 +52,7 @@ struct BinDev {
   float z_min, z_max;
   double r_max, rmax2;
   double inv_res;  // RN(1/res): certified-quotient fast path in grid_get_index_fast
+  float r_maxf;    // (float)r_max
   int cap;
 };
 
@@ -193,29 +194,31 @@ __device__ __forceinline__ bool grid_get_index_fast(const GridGeom &g, double in
   return true;
 }
 
-// oracle gvo_clip_end: parametric clip in continuous index space, fixed op order.
+// oracle gvo_clip_end: parametric clip in continuous index space; clip parameter in float
+// (IEEE float division), applied in double, fixed op order.
 __device__ __forceinline__ void clip_end(double oax, double oay, double eax, double eay, int nx,
                                          int ny, int &ex, int &ey)
 {
   const double nxd = (double)nx, nyd = (double)ny;
   const double dax = __dsub_rn(eax, oax), day = __dsub_rn(eay, oay);
-  double t = 1.0;
+  float t = 1.0f;
   if (eax < 0.0) {
-    const double tt = __ddiv_rn(__dsub_rn(0.0, oax), dax);
+    const float tt = __fdiv_rn(__double2float_rn(__dsub_rn(0.0, oax)), __double2float_rn(dax));
     if (tt < t) t = tt;
   } else if (eax >= nxd) {
-    const double tt = __ddiv_rn(__dsub_rn(nxd, oax), dax);
+    const float tt = __fdiv_rn(__double2float_rn(__dsub_rn(nxd, oax)), __double2float_rn(dax));
     if (tt < t) t = tt;
   }
   if (eay < 0.0) {
-    const double tt = __ddiv_rn(__dsub_rn(0.0, oay), day);
+    const float tt = __fdiv_rn(__double2float_rn(__dsub_rn(0.0, oay)), __double2float_rn(day));
     if (tt < t) t = tt;
   } else if (eay >= nyd) {
-    const double tt = __ddiv_rn(__dsub_rn(nyd, oay), day);
+    const float tt = __fdiv_rn(__double2float_rn(__dsub_rn(nyd, oay)), __double2float_rn(day));
     if (tt < t) t = tt;
   }
-  const double cx = __dadd_rn(oax, __dmul_rn(t, dax));
-  const double cy = __dadd_rn(oay, __dmul_rn(t, day));
+  const double td = (double)t;
+  const double cx = __dadd_rn(oax, __dmul_rn(td, dax));
+  const double cy = __dadd_rn(oay, __dmul_rn(td, day));
   ex = cx < 0.0 ? 0 : (cx >= nxd ? nx - 1 : __double2int_rz(cx));
   ey = cy < 0.0 ? 0 : (cy >= nyd ? ny - 1 : __double2int_rz(cy));
 }
@@ -238,7 +241,7 @@ __device__ __forceinline__ void bin_point(const BinDev &b, float x, float y, flo
     const double dx = __dsub_rn(px, b.ox), dy = __dsub_rn(py, b.oy);
     const double r2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
     if (r2 > b.rmax2) {
-      const double s = __ddiv_rn(b.r_max, __dsqrt_rn(r2));
+      const double s = (double)__fdiv_rn(b.r_maxf, __fsqrt_rn(__double2float_rn(r2)));
       px = __dadd_rn(b.ox, __dmul_rn(s, dx));
       py = __dadd_rn(b.oy, __dmul_rn(s, dy));
       hit_ok = false;
@@ -247,8 +250,8 @@ __device__ __forceinline__ void bin_point(const BinDev &b, float x, float y, flo
   }
   int ex, ey;
   if (!grid_get_index_fast(b.g, b.inv_res, px, py, ex, ey)) {
-    const double eax = index_coord(px, b.g.half_x, b.g.pos_x, b.g.res);
-    const double eay = index_coord(py, b.g.half_y, b.g.pos_y, b.g.res);
+    const double eax = -__dmul_rn(__dsub_rn(__dsub_rn(px, b.g.half_x), b.g.pos_x), b.inv_res);
+    const double eay = -__dmul_rn(__dsub_rn(__dsub_rn(py, b.g.half_y), b.g.pos_y), b.inv_res);
     clip_end(b.oax, b.oay, eax, eay, b.g.nx, b.g.ny, ex, ey);
     hit_ok = false;
     flags |= 4u;  // GV_F_CLIPPED
@@ -267,7 +270,55 @@ __device__ __forceinline__ void bin_point(const BinDev &b, float x, float y, flo
 // No barrier after the staging one: warps retire independently (projection and box tests
 // make per-warp work very uneven).
 // ----------------------------------------------------------------------------------
-template <bool FUSE, bool BIN>
+// R1 + R3 for one point against one camera: returns the label (index local to the camera's /
+// frame's box list, -1 = none); pix/u/v are the parity outputs.
+__device__ __forceinline__ int fuse_point(const CamDev &cam, int is_dense, float px, float py,
+                                          float pz, const float4 *s_box, int nb,
+                                          const unsigned long long *mset, int shift, int mtx,
+                                          int mwords, int &pix, float &u, float &v)
+{
+  int lab = -1;
+  pix = -1;
+  u = v = __int_as_float(0x7fc00000);
+  float X = px, Y = py, Z = pz;
+  // R1 (pcl::transformPointCloud: non-finite points pass through when !is_dense)
+  if (cam.has_T && (is_dense || finite3(X, Y, Z))) se3(cam.T, px, py, pz, X, Y, Z);
+  // ref: src/cloud_detections.cpp:264
+  if (finite3(X, Y, Z) && !(Z <= 0.001f)) {
+    project_point(cam, X, Y, Z, u, v);
+    // ref: :276  (float vs int -> the int is converted to float)
+    if (!(u < 0.0f || u >= cam.Wf || v < 0.0f || v >= cam.Hf)) {
+      const int iu = (int)u, iv = (int)v;
+      pix = iv * cam.W + iu;
+      // ref: :280-288 first box in list order wins, inclusive bounds.  Only boxes whose
+      // rectangle overlaps this point's image tile can contain it (k_box_masks); they are
+      // visited in ascending index order, so the first hit is the reference's.  The double
+      // bounds were rounded to float on the device (k_round_boxes) so these float compares
+      // decide exactly like the reference's float-vs-double compares.
+      if (nb > 0) {
+        const unsigned long long *mrow = mset + ((iv >> shift) * mtx + (iu >> shift)) * mwords;
+#pragma unroll 1
+        for (int w = 0; w < mwords && lab < 0; ++w) {
+          unsigned long long m = mrow[w];
+          while (m) {
+            const int b = w * 64 + __ffsll((long long)m) - 1;
+            m &= m - 1;
+            const float4 B = s_box[b];
+            if (u >= B.x && u <= B.z && v >= B.y && v <= B.w) {
+              lab = b;
+              break;
+            }
+          }
+        }
+      }
+    }
+  }
+  return lab;
+}
+
+// MULTI = false: one camera (index 0, every parameter a compile-time constant-bank operand);
+// MULTI = true: loop over a.ncam cameras of a rig (BASELINE config 4).
+template <bool FUSE, bool BIN, bool MULTI>
 __global__ void __launch_bounds__(kThreads) k_points(const __grid_constant__ PointArgs a)
 {
   extern __shared__ float4 s_dyn[];
@@ -289,6 +340,8 @@ __global__ void __launch_bounds__(kThreads) k_points(const __grid_constant__ Poi
     end = a.n;
   }
   if (end > start + (unsigned)a.tile_pts) end = start + (unsigned)a.tile_pts;
+  if (end <= start) return;
+  const unsigned cnt = (unsigned)(end - start);  // <= tile_pts: 32-bit tile-local indexing below
 
   if (FUSE) {
     // stage boxes + tile masks: batch mode -> this frame's set; otherwise every camera's set
@@ -302,95 +355,81 @@ __global__ void __launch_bounds__(kThreads) k_points(const __grid_constant__ Poi
     __syncthreads();
   }
 
+  const float *xp = a.x + start, *yp = a.y + start, *zp = a.z + start;
+  int16_t *lab_p = a.labels ? a.labels + start : nullptr;
+  int32_t *pix_p = a.pix ? a.pix + start : nullptr;
+  float *uv_p = a.uv ? a.uv + start : nullptr;
+  const int16_t *labin_p = (!FUSE && a.labels_in) ? a.labels_in + start : nullptr;
+  int32_t *cell_p = a.cell_out ? a.cell_out + start : nullptr;
+  uint8_t *flag_p = a.flags_out ? a.flags_out + start : nullptr;
+  const int nb0 = a.nframes > 0 ? be - bb : a.cam[0].box_end - a.cam[0].box_begin;
+
   // One point per thread per pass, next pass prefetched.  (A 4-points-per-thread version with
   // 128-bit loads ran out of instruction cache: 3.4k SASS instructions, 41% no-instruction
   // stalls in ncu; the path is issue-bound, not load-bound, so scalar coalesced loads win.)
-  unsigned long long i = start + threadIdx.x;
+  unsigned k = threadIdx.x;
   float nx = 0.0f, ny = 0.0f, nz = 0.0f;
-  if (i < end) {
-    nx = __ldg(a.x + i);
-    ny = __ldg(a.y + i);
-    nz = __ldg(a.z + i);
+  if (k < cnt) {
+    nx = __ldg(xp + k);
+    ny = __ldg(yp + k);
+    nz = __ldg(zp + k);
   }
 #pragma unroll 1
-  while (i < end) {
+  while (k < cnt) {
     const float px = nx, py = ny, pz = nz;
-    const unsigned long long inext = i + kThreads;
-    if (inext < end) {
-      nx = __ldg(a.x + inext);
-      ny = __ldg(a.y + inext);
-      nz = __ldg(a.z + inext);
+    const unsigned knext = k + kThreads;
+    if (knext < cnt) {
+      nx = __ldg(xp + knext);
+      ny = __ldg(yp + knext);
+      nz = __ldg(zp + knext);
     }
     int lab0 = -1;
 
     if (FUSE) {
-#pragma unroll 1
-      for (int c = 0; c < a.ncam; ++c) {
-        const CamDev &cam = a.cam[c];
-        // box list + mask set of this camera (single cloud) or of this tile's frame (batch)
-        const int b0 = a.nframes > 0 ? 0 : cam.box_begin;  // offset inside s_box
-        const int nb = a.nframes > 0 ? be - bb : cam.box_end - cam.box_begin;
-        const unsigned long long *mset = s_mask + (a.nframes > 0 ? 0 : c * a.mask_stride);
-        int lab = -1, pix = -1;
-        float u = __int_as_float(0x7fc00000), v = u;
-        float X = px, Y = py, Z = pz;
-        // R1 (pcl::transformPointCloud: non-finite points pass through when !is_dense)
-        if (cam.has_T && (a.is_dense || finite3(X, Y, Z))) se3(cam.T, px, py, pz, X, Y, Z);
-        // ref: src/cloud_detections.cpp:264
-        if (finite3(X, Y, Z) && !(Z <= 0.001f)) {
-          project_point(cam, X, Y, Z, u, v);
-          // ref: :276  (float vs int -> the int is converted to float)
-          if (!(u < 0.0f || u >= cam.Wf || v < 0.0f || v >= cam.Hf)) {
-            const int iu = (int)u, iv = (int)v;
-            pix = iv * cam.W + iu;
-            // ref: :280-288 first box in list order wins, inclusive bounds.  Only boxes whose
-            // rectangle overlaps this point's image tile can contain it (k_box_masks); they
-            // are visited in ascending index order, so the first hit is the reference's.
-            // The double bounds were rounded to float on the device (k_round_boxes) so these
-            // float compares decide exactly like the reference's float-vs-double compares.
-            if (nb > 0) {
-              const int shift = a.mask_shift[c];
-              const unsigned long long *mrow =
-                mset + ((iv >> shift) * a.mask_tx[c] + (iu >> shift)) * a.mask_words;
-#pragma unroll 1
-              for (int w = 0; w < a.mask_words && lab < 0; ++w) {
-                unsigned long long m = mrow[w];
-                while (m) {
-                  const int b = w * 64 + __ffsll((long long)m) - 1;
-                  m &= m - 1;
-                  const float4 B = s_box[b0 + b];
-                  if (u >= B.x && u <= B.z && v >= B.y && v <= B.w) {
-                    lab = b;
-                    break;
-                  }
-                }
-              }
-            }
-          }
+      if (!MULTI) {
+        int pix;
+        float u, v;
+        lab0 = fuse_point(a.cam[0], a.is_dense, px, py, pz, s_box + (a.nframes > 0 ? 0 : a.cam[0].box_begin),
+                          nb0, s_mask, a.mask_shift[0], a.mask_tx[0], a.mask_words, pix, u, v);
+        if (lab_p) lab_p[k] = (int16_t)lab0;
+        if (pix_p) pix_p[k] = pix;
+        if (uv_p) {
+          uv_p[k] = u;
+          uv_p[a.n + k] = v;
         }
-        if (c == 0) lab0 = lab;
-        const unsigned long long plane = (unsigned long long)c * a.n;
-        if (a.labels) a.labels[plane + i] = (int16_t)lab;
-        if (a.pix) a.pix[plane + i] = pix;
-        if (a.uv) {
-          a.uv[2 * plane + i] = u;
-          a.uv[2 * plane + a.n + i] = v;
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < a.ncam; ++c) {
+          const CamDev &cam = a.cam[c];
+          int pix;
+          float u, v;
+          const int lab = fuse_point(cam, a.is_dense, px, py, pz, s_box + cam.box_begin,
+                                     cam.box_end - cam.box_begin, s_mask + c * a.mask_stride,
+                                     a.mask_shift[c], a.mask_tx[c], a.mask_words, pix, u, v);
+          if (c == 0) lab0 = lab;
+          const unsigned long long plane = (unsigned long long)c * a.n;
+          if (lab_p) lab_p[plane + k] = (int16_t)lab;
+          if (pix_p) pix_p[plane + k] = pix;
+          if (uv_p) {
+            uv_p[2 * plane + k] = u;
+            uv_p[2 * plane + a.n + k] = v;
+          }
         }
       }
     }
 
     if (BIN) {
       int label = lab0;
-      if (!FUSE && a.labels_in) label = a.labels_in[i];
+      if (!FUSE && labin_p) label = labin_p[k];
       int cell;
       unsigned flags;
       bin_point(a.bin, px, py, pz, label, cell, flags);
       // one 64-bit RED per beam: low word counts beams ending in the cell, high word hits
       if (cell >= 0) atomicAdd(a.ends + cell, (flags & 2u) ? 0x100000001ull : 1ull);
-      if (a.cell_out) a.cell_out[i] = cell;
-      if (a.flags_out) a.flags_out[i] = (uint8_t)flags;
+      if (cell_p) cell_p[k] = cell;
+      if (flag_p) flag_p[k] = (uint8_t)flags;
     }
-    i = inext;
+    k = knext;
   }
 }
 

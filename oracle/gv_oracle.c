@@ -453,33 +453,42 @@ int32_t gvo_bresenham_cells(int32_t sx, int32_t sy, int32_t ex, int32_t ey, int3
 /* X1 + X2  bin + raycast, one beam at a time (brute force, no de-duplication) */
 /* ------------------------------------------------------------------------- */
 
-/* Off-map endpoints: clip the segment origin->endpoint in CONTINUOUS INDEX SPACE
- * (a = -(((p - 0.5 len) - P)/res), the negated grid_map indexVector) against
- * [0,nx) x [0,ny) with one parametric clip, every operation a separately rounded
- * IEEE double op in exactly this order.  This is a specification authored here
- * (SURVEY.md §8.a X2): the GPU kernel copies it op for op. */
+/* Off-map endpoints: clip the segment origin->endpoint in CONTINUOUS INDEX SPACE against
+ * [0,nx) x [0,ny) with one parametric clip.  The endpoint's index coordinate uses the
+ * reciprocal (a = -(((p - 0.5 len) - P) * (1/res))) and the clip parameter is computed in
+ * FLOAT (one IEEE float division per crossed side), then applied in double; every operation
+ * is a separately rounded IEEE op in exactly this order.  This is a specification authored
+ * here (the reference has no raycast): it only decides which boundary
+ * cell a free-space-only beam ends in, and the GPU kernel copies it op for op. */
+static inline double gvo_index_coord_mul(double p, double len, double pos, double inv_res)
+{
+  const double offset = 0.5 * len;
+  return -(((p - offset) - pos) * inv_res);
+}
+
 static inline void gvo_clip_end(double oax, double oay, double eax, double eay, int32_t nx,
                                 int32_t ny, int32_t *ex, int32_t *ey)
 {
   const double nxd = (double)nx, nyd = (double)ny;
   const double dax = eax - oax, day = eay - oay;
-  double t = 1.0;
+  float t = 1.0f;
   if (eax < 0.0) {
-    const double tt = (0.0 - oax) / dax;
+    const float tt = (float)(0.0 - oax) / (float)dax;
     if (tt < t) t = tt;
   } else if (eax >= nxd) {
-    const double tt = (nxd - oax) / dax;
+    const float tt = (float)(nxd - oax) / (float)dax;
     if (tt < t) t = tt;
   }
   if (eay < 0.0) {
-    const double tt = (0.0 - oay) / day;
+    const float tt = (float)(0.0 - oay) / (float)day;
     if (tt < t) t = tt;
   } else if (eay >= nyd) {
-    const double tt = (nyd - oay) / day;
+    const float tt = (float)(nyd - oay) / (float)day;
     if (tt < t) t = tt;
   }
-  const double cx = oax + t * dax;
-  const double cy = oay + t * day;
+  const double td = (double)t;
+  const double cx = oax + td * dax;
+  const double cy = oay + td * day;
   /* clamp in double first so the int cast is always defined */
   *ex = cx < 0.0 ? 0 : (cx >= nxd ? nx - 1 : (int32_t)cx);
   *ey = cy < 0.0 ? 0 : (cy >= nyd ? ny - 1 : (int32_t)cy);
@@ -497,6 +506,7 @@ int64_t gvo_accumulate(gvo_grid *g, const float T[16], const float *x, const flo
   const double oay = gvo_index_coord(oy, g->len_y, g->pos_y, g->res);
   const int cap = prm->r_max > 0.0;
   const double rmax2 = prm->r_max * prm->r_max;
+  const double inv_res = 1.0 / g->res;
   int64_t updates = 0;
 
   for (size_t i = 0; i < n; ++i) {
@@ -514,7 +524,9 @@ int64_t gvo_accumulate(gvo_grid *g, const float T[16], const float *x, const flo
       const double dx = px - ox, dy = py - oy;
       const double r2 = dx * dx + dy * dy;
       if (r2 > rmax2) {
-        const double s = prm->r_max / sqrt(r2);
+        /* scale factor in float (IEEE sqrt and divide), applied in double */
+        const float sf = (float)prm->r_max / sqrtf((float)r2);
+        const double s = (double)sf;
         px = ox + s * dx;
         py = oy + s * dy;
         hit_ok = 0;
@@ -523,8 +535,8 @@ int64_t gvo_accumulate(gvo_grid *g, const float T[16], const float *x, const flo
     }
     int32_t ex, ey;
     if (!gvo_grid_get_index(g, px, py, &ex, &ey)) {
-      const double eax = gvo_index_coord(px, g->len_x, g->pos_x, g->res);
-      const double eay = gvo_index_coord(py, g->len_y, g->pos_y, g->res);
+      const double eax = gvo_index_coord_mul(px, g->len_x, g->pos_x, inv_res);
+      const double eay = gvo_index_coord_mul(py, g->len_y, g->pos_y, inv_res);
       gvo_clip_end(oax, oay, eax, eay, g->nx, g->ny, &ex, &ey);
       hit_ok = 0;
       flags |= GVO_F_CLIPPED;

@@ -1,0 +1,3 @@
+// Stand-in for <geometry_msgs/msg/pose.hpp> (absent in the build container): everything lives in gv_standins.hpp.
+#pragma once
+#include "gv_standins.hpp"
