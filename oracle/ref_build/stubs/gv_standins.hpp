@@ -113,6 +113,8 @@ struct MatrixXf {
   }
   int rows() const { return r; }
   int cols() const { return c; }
+  float *data() { return d.data(); }
+  const float *data() const { return d.data(); }
   float &operator()(int i, int j) { return d[(size_t)i + (size_t)j * r]; }
   float operator()(int i, int j) const { return d[(size_t)i + (size_t)j * r]; }
   void setConstant(float v) { std::fill(d.begin(), d.end(), v); }
