@@ -241,10 +241,10 @@ int set_bin_params(gv_ctx *ctx, const gv_accum_params *prm, BinDev *out)
   out->z_min = prm->z_min;
   out->z_max = prm->z_max;
   out->cap = prm->r_max > 0.0 ? 1 : 0;
-  out->r_max = prm->r_max;
-  out->rmax2 = prm->r_max * prm->r_max;
-  out->inv_res = 1.0 / ctx->g.res;
-  out->r_maxf = (float)prm->r_max;
+  // float geometry of free-space-only beams: the same single-rounded float expressions as the
+  // specification (oracle gvo_beam_geom_init); host floats are IEEE binary32, no contraction
+  out->rmaxf = (float)prm->r_max;
+  out->rmax2f = out->rmaxf * out->rmaxf;
   return GV_OK;
 }
 
@@ -261,10 +261,13 @@ int note_beams(gv_ctx *ctx, unsigned long long n)
 int launch_points(gv_ctx *ctx, bool fuse, bool bin, PointArgs &a, unsigned ntiles, size_t smem)
 {
   if (ntiles == 0) return GV_OK;
-  if (fuse && bin) k_points<true, true, false><<<ntiles, kThreads, smem, ctx->stream>>>(a);
-  else if (fuse && a.ncam > 1) k_points<true, false, true><<<ntiles, kThreads, smem, ctx->stream>>>(a);
-  else if (fuse) k_points<true, false, false><<<ntiles, kThreads, smem, ctx->stream>>>(a);
-  else k_points<false, true, false><<<ntiles, kThreads, smem, ctx->stream>>>(a);
+  const bool exact_uv = a.pix != nullptr || a.uv != nullptr;
+  if (fuse && bin) k_points<true, true, false, false><<<ntiles, kThreads, smem, ctx->stream>>>(a);
+  else if (fuse && a.ncam > 1 && exact_uv) k_points<true, false, true, true><<<ntiles, kThreads, smem, ctx->stream>>>(a);
+  else if (fuse && a.ncam > 1) k_points<true, false, true, false><<<ntiles, kThreads, smem, ctx->stream>>>(a);
+  else if (fuse && exact_uv) k_points<true, false, false, true><<<ntiles, kThreads, smem, ctx->stream>>>(a);
+  else if (fuse) k_points<true, false, false, false><<<ntiles, kThreads, smem, ctx->stream>>>(a);
+  else k_points<false, true, false, false><<<ntiles, kThreads, smem, ctx->stream>>>(a);
   GV_LAUNCH_CHECK();
   return GV_OK;
 }
@@ -345,9 +348,13 @@ int fuse_dev_impl(gv_ctx *ctx, const float *d_x, const float *d_y, const float *
   const size_t smem = (size_t)a.smem_boxes * sizeof(float4) +
                       (size_t)ctx->ncam * a.mask_stride * sizeof(unsigned long long);
   if (smem > 48 * 1024) {
-    GV_CUDA(cudaFuncSetAttribute(k_points<true, false, false>,
+    GV_CUDA(cudaFuncSetAttribute(k_points<true, false, false, false>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GV_CUDA(cudaFuncSetAttribute(k_points<true, false, true>,
+    GV_CUDA(cudaFuncSetAttribute(k_points<true, false, false, true>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GV_CUDA(cudaFuncSetAttribute(k_points<true, false, true, false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GV_CUDA(cudaFuncSetAttribute(k_points<true, false, true, true>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   return launch_points(ctx, true, false, a, blocks_for(n, a.tile_pts), smem);
@@ -481,15 +488,30 @@ int refresh_origin(gv_ctx *ctx)
   GV_CUDA(cudaMemcpyAsync(&o, d_o, sizeof(o), cudaMemcpyDeviceToHost, ctx->stream));
   GV_CUDA(cudaStreamSynchronize(ctx->stream));
   BinDev &b = ctx->bin;
+  const GridGeom &g = ctx->g;
   copy_T12(b.T, ctx->Tb);
-  b.g = ctx->g;
-  b.ox = ox;
-  b.oy = oy;
-  b.oax = o.oax;
-  b.oay = o.oay;
+  b.g = g;
   b.sx = o.sx;
   b.sy = o.sy;
   b.origin_ok = o.ok;
+  b.oxf = ctx->Tb[3];
+  b.oyf = ctx->Tb[7];
+  b.c0xf = (float)(0.5 * g.len_x + g.pos_x);
+  b.c0yf = (float)(0.5 * g.len_y + g.pos_y);
+  b.inv_resf = (float)(1.0 / g.res);
+  const float dxo = b.c0xf - b.oxf, dyo = b.c0yf - b.oyf;
+  b.oaxf = dxo * b.inv_resf;
+  b.oayf = dyo * b.inv_resf;
+  // certified fixed-point index (grid_get_index_cert): needs 8*2^-53*(|p|+half+|pos|)/res < 2^-21
+  // for every in-map p, i.e. (half + |pos|)/res < ~2^28; otherwise always the exact path
+  b.c0xd = g.half_x + g.pos_x;
+  b.c0yd = g.half_y + g.pos_y;
+  b.mres = 1048576.0 / g.res;
+  b.klim_x = (long long)g.nx << 20;
+  b.klim_y = (long long)g.ny << 20;
+  const double span = (g.half_x + std::fabs(g.pos_x) > g.half_y + std::fabs(g.pos_y)
+                         ? g.half_x + std::fabs(g.pos_x) : g.half_y + std::fabs(g.pos_y)) / g.res;
+  b.fast_index_ok = span < 134217728.0 ? 1 : 0;
   return GV_OK;
 }
 
@@ -670,6 +692,14 @@ int gv_set_cameras(gv_ctx *ctx, int ncam, const double *K, const float *T_cam_li
     d.Wf = (float)d.W;
     d.Hf = (float)d.H;
     d.canon = is_canonical_K(d.K) ? 1 : 0;
+    // certified float projection constants: E(q) = e6*|q| + e0 = 2^-22 (6|q| + |c| + 1)
+    d.fxf = (float)d.K[0];
+    d.fyf = (float)d.K[4];
+    d.cxf = (float)d.K[2];
+    d.cyf = (float)d.K[5];
+    d.e6 = 6.0f * 2.384185791015625e-07f;
+    d.e0u = 2.384185791015625e-07f * (std::fabs(d.cxf) + 1.0f) * 1.0001f;
+    d.e0v = 2.384185791015625e-07f * (std::fabs(d.cyf) + 1.0f) * 1.0001f;
   }
   ctx->ncam = ncam;
   return GV_OK;
@@ -1212,7 +1242,7 @@ static int process_batch_impl(gv_ctx *ctx, const float *px, const float *py, con
   const size_t smem = (size_t)max_boxes * sizeof(float4) +
                       (size_t)a.mask_stride * sizeof(unsigned long long);
   if (smem > 48 * 1024)
-    GV_CUDA(cudaFuncSetAttribute(k_points<true, true, false>,
+    GV_CUDA(cudaFuncSetAttribute(k_points<true, true, false, false>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
   if (points_on_device) {

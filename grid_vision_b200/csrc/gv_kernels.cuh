@@ -34,6 +34,10 @@ struct CamDev {
   int has_T;     // 0: cloud already in the camera frame
   int canon;     // K == [fx 0 cx; 0 fy cy; 0 0 1] with float-representable entries
   int box_begin, box_end;
+  // certified float projection (canonical K only): exact float copies of fx, fy, cx, cy and the
+  // constants of the error bound E(q) = e6*|q| + e0 (see fuse_point_fast)
+  float fxf, fyf, cxf, cyf;
+  float e6, e0u, e0v;
 };
 
 struct GridGeom {
@@ -44,16 +48,17 @@ struct GridGeom {
 struct BinDev {
   float T[12];  // row-major 3x4 T_base<-lidar
   GridGeom g;
-  double ox, oy;    // sensor origin in the base frame (translation column, promoted)
-  double oax, oay;  // its continuous index coordinates
-  int sx, sy;       // origin cell
+  int sx, sy;  // origin cell (grid_map getIndex of the sensor origin)
   int origin_ok;
   int occ_mode, use_z_gate;
   float z_min, z_max;
-  double r_max, rmax2;
-  double inv_res;  // RN(1/res): certified-quotient fast path in grid_get_index_fast
-  float r_maxf;    // (float)r_max
+  // float geometry of free-space-only beams (oracle gvo_beam_geom)
+  float oxf, oyf, c0xf, c0yf, inv_resf, oaxf, oayf, rmaxf, rmax2f;
   int cap;
+  // certified fixed-point index: k = trunc((c0 - p) * (2^20 / res)) holds cell and fraction
+  double c0xd, c0yd, mres;
+  long long klim_x, klim_y;  // size << 20
+  int fast_index_ok;
 };
 
 struct PointArgs {
@@ -165,62 +170,68 @@ __device__ __forceinline__ bool grid_get_index(const GridGeom &g, double px, dou
   return true;
 }
 
-// Same result as grid_get_index, without the two double divisions in the common case.
-// The contract is index = trunc(-RN(t/res)) with t = (p - half) - pos.  a' = -(t * RN(1/res))
-// differs from -RN(t/res) by at most |a'| * 3.4e-16 (< 1e-6 for any int32 index), so when a'
-// is farther than 1e-6 from an integer both truncate to the same cell; otherwise (a point on
-// a cell boundary to ~1e-6 cells) the exact division decides.  Bit-identical by construction.
-__device__ __forceinline__ int trunc_index(double t, double res, double inv_res)
+// Certified fast version of grid_get_index for float positions (X1).  The contract is
+//   inside  <=>  0 <= -((p - pos) - half) < len  (per axis, double)      [checkIfPositionWithinMap]
+//   index   =   trunc(-(((p - half) - pos) / res))                       [getIndexFromPosition]
+// Fast path: a' = (c0 - p) * (2^20/res) in double with c0 = RN(half + pos); k = trunc(a') is a
+// 44.20 fixed-point image of the exact index coordinate a.  a' / 2^20 differs from the
+// reference's rounded a (and q/res from a) by at most 8 * 2^-53 * (|p| + half + |pos|) / res,
+// which the host guarantees is below 2^-21 cells (fast_index_ok), so when the 20-bit fraction
+// of k lies in [16, 2^20 - 16] both formulas truncate to the same cell, and when
+// 16 <= k < (size << 20) - 16 the point is certainly inside.  Anything else (a point within
+// 1.5e-5 cells of a cell or map boundary, NaN, a huge coordinate) takes the exact path.
+// Returns true with (ix,iy) when inside; false when outside.  Bit-identical by construction.
+__device__ __forceinline__ bool grid_get_index_cert(const BinDev &b, float pxf, float pyf, int &ix,
+                                                    int &iy)
 {
-  const double a = -__dmul_rn(t, inv_res);
-  const int i = __double2int_rz(a);
-  const double f = __dsub_rn(a, (double)i);
-  if (f > 1e-6 && f < 1.0 - 1e-6) return i;
-  return __double2int_rz(-__ddiv_rn(t, res));
+  if (b.fast_index_ok) {
+    const long long kx = __double2ll_rz(__dmul_rn(__dsub_rn(b.c0xd, (double)pxf), b.mres));
+    const long long ky = __double2ll_rz(__dmul_rn(__dsub_rn(b.c0yd, (double)pyf), b.mres));
+    const unsigned fx = (unsigned)kx & 0xfffffu, fy = (unsigned)ky & 0xfffffu;
+    const bool frac_ok = (fx - 16u <= 0xfffffu - 32u) && (fy - 16u <= 0xfffffu - 32u);
+    if (frac_ok && kx >= 16 && ky >= 16 && kx < b.klim_x - 16 && ky < b.klim_y - 16) {
+      ix = (int)(kx >> 20);
+      iy = (int)(ky >> 20);
+      return true;
+    }
+    // certainly outside: more than 16/2^20 cells beyond an edge on some axis
+    if (kx < -16 || ky < -16 || kx >= b.klim_x + 16 || ky >= b.klim_y + 16) {
+      // (NaN converts to 0 and never lands here)
+      return false;
+    }
+  }
+  return grid_get_index(b.g, (double)pxf, (double)pyf, ix, iy);
 }
 
-__device__ __forceinline__ bool grid_get_index_fast(const GridGeom &g, double inv_res, double px,
-                                                    double py, int &ix, int &iy)
+__device__ __forceinline__ int clamp_cell(float c, int n)
 {
-  const double qx = -__dsub_rn(__dsub_rn(px, g.pos_x), g.half_x);
-  const double qy = -__dsub_rn(__dsub_rn(py, g.pos_y), g.half_y);
-  if (!(qx >= 0.0 && qy >= 0.0 && qx < g.len_x && qy < g.len_y)) return false;
-  // inside the map rectangle |a| <= size + 1, so the int conversions below are in range
-  const int i = trunc_index(__dsub_rn(__dsub_rn(px, g.half_x), g.pos_x), g.res, inv_res);
-  const int j = trunc_index(__dsub_rn(__dsub_rn(py, g.half_y), g.pos_y), g.res, inv_res);
-  if (!(i >= 0 && j >= 0 && i < g.nx && j < g.ny)) return false;
-  ix = i;
-  iy = j;
-  return true;
+  return c >= 0.0f ? (c >= (float)n ? n - 1 : (int)c) : 0;  // NaN -> 0
 }
 
-// oracle gvo_clip_end: parametric clip in continuous index space; clip parameter in float
-// (IEEE float division), applied in double, fixed op order.
-__device__ __forceinline__ void clip_end(double oax, double oay, double eax, double eay, int nx,
-                                         int ny, int &ex, int &ey)
+// oracle gvo_clip_end: all-float parametric clip in index space, one rounded op per step.
+__device__ __forceinline__ void clip_end(const BinDev &b, float pxf, float pyf, int &ex, int &ey)
 {
-  const double nxd = (double)nx, nyd = (double)ny;
-  const double dax = __dsub_rn(eax, oax), day = __dsub_rn(eay, oay);
+  const float nxf = (float)b.g.nx, nyf = (float)b.g.ny;
+  const float eax = __fmul_rn(__fsub_rn(b.c0xf, pxf), b.inv_resf);
+  const float eay = __fmul_rn(__fsub_rn(b.c0yf, pyf), b.inv_resf);
+  const float dax = __fsub_rn(eax, b.oaxf), day = __fsub_rn(eay, b.oayf);
   float t = 1.0f;
-  if (eax < 0.0) {
-    const float tt = __fdiv_rn(__double2float_rn(__dsub_rn(0.0, oax)), __double2float_rn(dax));
+  if (eax < 0.0f) {
+    const float tt = __fdiv_rn(__fsub_rn(0.0f, b.oaxf), dax);
     if (tt < t) t = tt;
-  } else if (eax >= nxd) {
-    const float tt = __fdiv_rn(__double2float_rn(__dsub_rn(nxd, oax)), __double2float_rn(dax));
-    if (tt < t) t = tt;
-  }
-  if (eay < 0.0) {
-    const float tt = __fdiv_rn(__double2float_rn(__dsub_rn(0.0, oay)), __double2float_rn(day));
-    if (tt < t) t = tt;
-  } else if (eay >= nyd) {
-    const float tt = __fdiv_rn(__double2float_rn(__dsub_rn(nyd, oay)), __double2float_rn(day));
+  } else if (eax >= nxf) {
+    const float tt = __fdiv_rn(__fsub_rn(nxf, b.oaxf), dax);
     if (tt < t) t = tt;
   }
-  const double td = (double)t;
-  const double cx = __dadd_rn(oax, __dmul_rn(td, dax));
-  const double cy = __dadd_rn(oay, __dmul_rn(td, day));
-  ex = cx < 0.0 ? 0 : (cx >= nxd ? nx - 1 : __double2int_rz(cx));
-  ey = cy < 0.0 ? 0 : (cy >= nyd ? ny - 1 : __double2int_rz(cy));
+  if (eay < 0.0f) {
+    const float tt = __fdiv_rn(__fsub_rn(0.0f, b.oayf), day);
+    if (tt < t) t = tt;
+  } else if (eay >= nyf) {
+    const float tt = __fdiv_rn(__fsub_rn(nyf, b.oayf), day);
+    if (tt < t) t = tt;
+  }
+  ex = clamp_cell(__fadd_rn(b.oaxf, __fmul_rn(t, dax)), b.g.nx);
+  ey = clamp_cell(__fadd_rn(b.oayf, __fmul_rn(t, day)), b.g.ny);
 }
 
 // X1: one beam -> (end cell, flags).  Mirrors the per-point body of oracle gvo_accumulate.
@@ -234,25 +245,22 @@ __device__ __forceinline__ void bin_point(const BinDev &b, float x, float y, flo
   float bx, by, bz;
   se3(b.T, x, y, z, bx, by, bz);
   if (!finite3(bx, by, bz)) return;
-  double px = (double)bx, py = (double)by;
   bool hit_ok = true;
   flags = 1u;  // GV_F_VALID
   if (b.cap) {
-    const double dx = __dsub_rn(px, b.ox), dy = __dsub_rn(py, b.oy);
-    const double r2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-    if (r2 > b.rmax2) {
-      const double s = (double)__fdiv_rn(b.r_maxf, __fsqrt_rn(__double2float_rn(r2)));
-      px = __dadd_rn(b.ox, __dmul_rn(s, dx));
-      py = __dadd_rn(b.oy, __dmul_rn(s, dy));
+    const float dx = __fsub_rn(bx, b.oxf), dy = __fsub_rn(by, b.oyf);
+    const float r2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+    if (r2 > b.rmax2f) {
+      const float sf = __fdiv_rn(b.rmaxf, __fsqrt_rn(r2));
+      bx = __fadd_rn(b.oxf, __fmul_rn(sf, dx));
+      by = __fadd_rn(b.oyf, __fmul_rn(sf, dy));
       hit_ok = false;
       flags |= 8u;  // GV_F_RANGECAP
     }
   }
   int ex, ey;
-  if (!grid_get_index_fast(b.g, b.inv_res, px, py, ex, ey)) {
-    const double eax = -__dmul_rn(__dsub_rn(__dsub_rn(px, b.g.half_x), b.g.pos_x), b.inv_res);
-    const double eay = -__dmul_rn(__dsub_rn(__dsub_rn(py, b.g.half_y), b.g.pos_y), b.inv_res);
-    clip_end(b.oax, b.oay, eax, eay, b.g.nx, b.g.ny, ex, ey);
+  if (!grid_get_index_cert(b, bx, by, ex, ey)) {
+    clip_end(b, bx, by, ex, ey);
     hit_ok = false;
     flags |= 4u;  // GV_F_CLIPPED
   }
@@ -270,8 +278,55 @@ __device__ __forceinline__ void bin_point(const BinDev &b, float x, float y, flo
 // No barrier after the staging one: warps retire independently (projection and box tests
 // make per-warp work very uneven).
 // ----------------------------------------------------------------------------------
+// Certified float version of R3's decisions for one camera-frame point (canonical K only).
+// q = (fx*X + cx*Z)/Z evaluated in binary32 (one multiply, one FMA, one 2-ulp division) is within
+//   |q - u_ref| <= 1.01 * 2^-24 * (|cx| + 6|u|)
+// of the reference's u_ref = (float)((double)(fx*X + cx*Z) / Z): the product cx*Z and the FMA
+// each contribute one half-ulp relative error (the first scaled by |cx*Z|/|Z| = |cx|, the second
+// by |u|), the division 4 * 2^-24 |u|, and the reference's own narrowing to float 2^-24 |u|.
+// E(q) = e6*|q| + e0 with e6 = 6 * 2^-22, e0 = 2^-22 (|cx| + 1) is four times that bound.  A
+// decision (u < 0, u >= W, u >= x_min, u <= x_max, which 32-px tile) is taken here only if it
+// is the same for every value in [q - E, q + E]; otherwise the function returns false and the
+// caller evaluates the exact FP64 path for this point.  Returns true with the label set.
+__device__ __forceinline__ bool fuse_point_fast(const CamDev &cam, float X, float Y, float Z,
+                                                const float4 *s_box, int nb,
+                                                const unsigned long long *mset, int shift, int mtx,
+                                                int mwords, int &lab)
+{
+  lab = -1;
+  const float q = __fdividef(fmaf(cam.fxf, X, cam.cxf * Z), Z);
+  const float r = __fdividef(fmaf(cam.fyf, Y, cam.cyf * Z), Z);
+  const float Eu = fmaf(fabsf(q), cam.e6, cam.e0u), Ev = fmaf(fabsf(r), cam.e6, cam.e0v);
+  const float ql = q - Eu, qh = q + Eu, rl = r - Ev, rh = r + Ev;
+  // ref: src/cloud_detections.cpp:276 image test
+  if (!(ql >= 0.0f && qh < cam.Wf && rl >= 0.0f && rh < cam.Hf)) {
+    // certainly outside the image -> no label; else too close to an image edge to call
+    return qh < 0.0f || ql >= cam.Wf || rh < 0.0f || rl >= cam.Hf;
+  }
+  if (nb <= 0) return true;
+  const int tu = (int)ql >> shift, tv = (int)rl >> shift;
+  if (tu != ((int)qh >> shift) || tv != ((int)rh >> shift)) return false;  // straddles a tile edge
+  const unsigned long long *mrow = mset + (tv * mtx + tu) * mwords;
+#pragma unroll 1
+  for (int w = 0; w < mwords; ++w) {
+    unsigned long long m = mrow[w];
+    while (m) {
+      const int b = w * 64 + __ffsll((long long)m) - 1;
+      m &= m - 1;
+      const float4 B = s_box[b];
+      if (ql >= B.x && qh <= B.z && rl >= B.y && rh <= B.w) {  // certainly inside: first match
+        lab = b;
+        return true;
+      }
+      if (!(qh < B.x || ql > B.z || rh < B.y || rl > B.w)) return false;  // not certainly outside
+    }
+  }
+  return true;
+}
+
 // R1 + R3 for one point against one camera: returns the label (index local to the camera's /
-// frame's box list, -1 = none); pix/u/v are the parity outputs.
+// frame's box list, -1 = none); pix/u/v are the parity outputs (EXACT_UV: always the FP64 path).
+template <bool EXACT_UV>
 __device__ __forceinline__ int fuse_point(const CamDev &cam, int is_dense, float px, float py,
                                           float pz, const float4 *s_box, int nb,
                                           const unsigned long long *mset, int shift, int mtx,
@@ -285,6 +340,14 @@ __device__ __forceinline__ int fuse_point(const CamDev &cam, int is_dense, float
   if (cam.has_T && (is_dense || finite3(X, Y, Z))) se3(cam.T, px, py, pz, X, Y, Z);
   // ref: src/cloud_detections.cpp:264
   if (finite3(X, Y, Z) && !(Z <= 0.001f)) {
+    if (!EXACT_UV && cam.canon) {
+      // magnitudes the error analysis (and __fdividef) covers; anything larger goes exact
+      const float big = 1.0e15f;
+      if (fabsf(X) < big && fabsf(Y) < big && Z < big &&
+          fuse_point_fast(cam, X, Y, Z, s_box, nb, mset, shift, mtx, mwords, lab))
+        return lab;
+      lab = -1;
+    }
     project_point(cam, X, Y, Z, u, v);
     // ref: :276  (float vs int -> the int is converted to float)
     if (!(u < 0.0f || u >= cam.Wf || v < 0.0f || v >= cam.Hf)) {
@@ -318,7 +381,8 @@ __device__ __forceinline__ int fuse_point(const CamDev &cam, int is_dense, float
 
 // MULTI = false: one camera (index 0, every parameter a compile-time constant-bank operand);
 // MULTI = true: loop over a.ncam cameras of a rig (BASELINE config 4).
-template <bool FUSE, bool BIN, bool MULTI>
+// EXACT_UV = true: u,v / pixel parity outputs requested, projection always in FP64.
+template <bool FUSE, bool BIN, bool MULTI, bool EXACT_UV>
 __global__ void __launch_bounds__(kThreads) k_points(const __grid_constant__ PointArgs a)
 {
   extern __shared__ float4 s_dyn[];
@@ -389,13 +453,15 @@ __global__ void __launch_bounds__(kThreads) k_points(const __grid_constant__ Poi
       if (!MULTI) {
         int pix;
         float u, v;
-        lab0 = fuse_point(a.cam[0], a.is_dense, px, py, pz, s_box + (a.nframes > 0 ? 0 : a.cam[0].box_begin),
+        lab0 = fuse_point<EXACT_UV>(a.cam[0], a.is_dense, px, py, pz, s_box + (a.nframes > 0 ? 0 : a.cam[0].box_begin),
                           nb0, s_mask, a.mask_shift[0], a.mask_tx[0], a.mask_words, pix, u, v);
         if (lab_p) lab_p[k] = (int16_t)lab0;
-        if (pix_p) pix_p[k] = pix;
-        if (uv_p) {
-          uv_p[k] = u;
-          uv_p[a.n + k] = v;
+        if (EXACT_UV) {
+          if (pix_p) pix_p[k] = pix;
+          if (uv_p) {
+            uv_p[k] = u;
+            uv_p[a.n + k] = v;
+          }
         }
       } else {
 #pragma unroll 1
@@ -403,16 +469,18 @@ __global__ void __launch_bounds__(kThreads) k_points(const __grid_constant__ Poi
           const CamDev &cam = a.cam[c];
           int pix;
           float u, v;
-          const int lab = fuse_point(cam, a.is_dense, px, py, pz, s_box + cam.box_begin,
+          const int lab = fuse_point<EXACT_UV>(cam, a.is_dense, px, py, pz, s_box + cam.box_begin,
                                      cam.box_end - cam.box_begin, s_mask + c * a.mask_stride,
                                      a.mask_shift[c], a.mask_tx[c], a.mask_words, pix, u, v);
           if (c == 0) lab0 = lab;
           const unsigned long long plane = (unsigned long long)c * a.n;
           if (lab_p) lab_p[plane + k] = (int16_t)lab;
-          if (pix_p) pix_p[plane + k] = pix;
-          if (uv_p) {
-            uv_p[2 * plane + k] = u;
-            uv_p[2 * plane + a.n + k] = v;
+          if (EXACT_UV) {
+            if (pix_p) pix_p[plane + k] = pix;
+            if (uv_p) {
+              uv_p[2 * plane + k] = u;
+              uv_p[2 * plane + a.n + k] = v;
+            }
           }
         }
       }
@@ -1032,7 +1100,6 @@ __global__ void k_round_boxes(const BoxRaw *__restrict__ in, int n, float4 *__re
 
 // sensor origin -> start cell and continuous index coordinates (single thread)
 struct OriginOut {
-  double oax, oay;
   int sx, sy, ok, pad;
 };
 
@@ -1043,8 +1110,6 @@ __global__ void k_origin_setup(double ox, double oy, const __grid_constant__ Gri
   o.sx = o.sy = -1;
   o.pad = 0;
   o.ok = grid_get_index(g, ox, oy, o.sx, o.sy) ? 1 : 0;
-  o.oax = index_coord(ox, g.half_x, g.pos_x, g.res);
-  o.oay = index_coord(oy, g.half_y, g.pos_y, g.res);
   *out = o;
 }
 

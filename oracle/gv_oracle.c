@@ -453,45 +453,68 @@ int32_t gvo_bresenham_cells(int32_t sx, int32_t sy, int32_t ex, int32_t ey, int3
 /* X1 + X2  bin + raycast, one beam at a time (brute force, no de-duplication) */
 /* ------------------------------------------------------------------------- */
 
-/* Off-map endpoints: clip the segment origin->endpoint in CONTINUOUS INDEX SPACE against
- * [0,nx) x [0,ny) with one parametric clip.  The endpoint's index coordinate uses the
- * reciprocal (a = -(((p - 0.5 len) - P) * (1/res))) and the clip parameter is computed in
- * FLOAT (one IEEE float division per crossed side), then applied in double; every operation
- * is a separately rounded IEEE op in exactly this order.  This is a specification authored
- * here (the reference has no raycast): it only decides which boundary
- * cell a free-space-only beam ends in, and the GPU kernel copies it op for op. */
-static inline double gvo_index_coord_mul(double p, double len, double pos, double inv_res)
+/* Geometry of free-space-only beams (range-capped and/or off-map endpoints) — a
+ * specification authored here (the reference has no raycast), chosen so that
+ * it is cheap on the GPU and bit-reproducible everywhere: every step is ONE separately rounded
+ * IEEE binary32 operation (add, sub, mul, div, sqrt — no FMA), in exactly this order.
+ *   range cap   d = p - o;  r2 = dx*dx + dy*dy;  capped iff r2 > rmax*rmax;
+ *               p' = o + (rmax / sqrt(r2)) * d
+ *   index coord a(p) = (c0 - p) * inv_res,  c0 = (float)(0.5*len + pos), inv_res = (float)(1/res)
+ *   clip        one parametric clip of o_a -> e_a against [0,nx) x [0,ny), end cell = the
+ *               truncated clipped coordinate, clamped into the map (NaN clamps to 0).
+ * Only WHETHER an endpoint is inside the map is decided by the exact grid_map getIndex. */
+typedef struct {
+  float oxf, oyf;       /* sensor origin (translation column of T_base<-lidar) */
+  float c0xf, c0yf, inv_resf;
+  float oaxf, oayf;     /* a(origin) */
+  float rmaxf, rmax2f;
+} gvo_beam_geom;
+
+static inline void gvo_beam_geom_init(gvo_beam_geom *b, const gvo_grid *g, const float T[16],
+                                      double r_max)
 {
-  const double offset = 0.5 * len;
-  return -(((p - offset) - pos) * inv_res);
+  b->oxf = T[3];
+  b->oyf = T[7];
+  b->c0xf = (float)(0.5 * g->len_x + g->pos_x);
+  b->c0yf = (float)(0.5 * g->len_y + g->pos_y);
+  b->inv_resf = (float)(1.0 / g->res);
+  b->oaxf = (b->c0xf - b->oxf) * b->inv_resf;
+  b->oayf = (b->c0yf - b->oyf) * b->inv_resf;
+  b->rmaxf = (float)r_max;
+  b->rmax2f = b->rmaxf * b->rmaxf;
 }
 
-static inline void gvo_clip_end(double oax, double oay, double eax, double eay, int32_t nx,
+static inline int32_t gvo_clamp_cell(float c, int32_t n)
+{
+  /* written so that NaN falls to 0 and the int cast is always defined */
+  return c >= 0.0f ? (c >= (float)n ? n - 1 : (int32_t)c) : 0;
+}
+
+static inline void gvo_clip_end(const gvo_beam_geom *b, float pxf, float pyf, int32_t nx,
                                 int32_t ny, int32_t *ex, int32_t *ey)
 {
-  const double nxd = (double)nx, nyd = (double)ny;
-  const double dax = eax - oax, day = eay - oay;
+  const float nxf = (float)nx, nyf = (float)ny;
+  const float eax = (b->c0xf - pxf) * b->inv_resf;
+  const float eay = (b->c0yf - pyf) * b->inv_resf;
+  const float dax = eax - b->oaxf, day = eay - b->oayf;
   float t = 1.0f;
-  if (eax < 0.0) {
-    const float tt = (float)(0.0 - oax) / (float)dax;
+  if (eax < 0.0f) {
+    const float tt = (0.0f - b->oaxf) / dax;
     if (tt < t) t = tt;
-  } else if (eax >= nxd) {
-    const float tt = (float)(nxd - oax) / (float)dax;
-    if (tt < t) t = tt;
-  }
-  if (eay < 0.0) {
-    const float tt = (float)(0.0 - oay) / (float)day;
-    if (tt < t) t = tt;
-  } else if (eay >= nyd) {
-    const float tt = (float)(nyd - oay) / (float)day;
+  } else if (eax >= nxf) {
+    const float tt = (nxf - b->oaxf) / dax;
     if (tt < t) t = tt;
   }
-  const double td = (double)t;
-  const double cx = oax + td * dax;
-  const double cy = oay + td * day;
-  /* clamp in double first so the int cast is always defined */
-  *ex = cx < 0.0 ? 0 : (cx >= nxd ? nx - 1 : (int32_t)cx);
-  *ey = cy < 0.0 ? 0 : (cy >= nyd ? ny - 1 : (int32_t)cy);
+  if (eay < 0.0f) {
+    const float tt = (0.0f - b->oayf) / day;
+    if (tt < t) t = tt;
+  } else if (eay >= nyf) {
+    const float tt = (nyf - b->oayf) / day;
+    if (tt < t) t = tt;
+  }
+  const float mx = t * dax, my = t * day;
+  *ex = gvo_clamp_cell(b->oaxf + mx, nx);
+  *ey = gvo_clamp_cell(b->oayf + my, ny);
 }
 
 int64_t gvo_accumulate(gvo_grid *g, const float T[16], const float *x, const float *y,
@@ -502,11 +525,9 @@ int64_t gvo_accumulate(gvo_grid *g, const float T[16], const float *x, const flo
   const double ox = (double)T[3], oy = (double)T[7];
   int32_t sx, sy;
   const int origin_ok = gvo_grid_get_index(g, ox, oy, &sx, &sy);
-  const double oax = gvo_index_coord(ox, g->len_x, g->pos_x, g->res);
-  const double oay = gvo_index_coord(oy, g->len_y, g->pos_y, g->res);
   const int cap = prm->r_max > 0.0;
-  const double rmax2 = prm->r_max * prm->r_max;
-  const double inv_res = 1.0 / g->res;
+  gvo_beam_geom bg;
+  gvo_beam_geom_init(&bg, g, T, prm->r_max);
   int64_t updates = 0;
 
   for (size_t i = 0; i < n; ++i) {
@@ -517,27 +538,26 @@ int64_t gvo_accumulate(gvo_grid *g, const float T[16], const float *x, const flo
     float pb[3];
     gvo_se3(T, x[i], y[i], z[i], pb); /* X1: p_base = T_base<-lidar * p, R1 op order */
     if (!gvo_finite3(pb[0], pb[1], pb[2])) continue;
-    double px = (double)pb[0], py = (double)pb[1];
+    float pxf = pb[0], pyf = pb[1];
     int hit_ok = 1;
     uint8_t flags = GVO_F_VALID;
     if (cap) {
-      const double dx = px - ox, dy = py - oy;
-      const double r2 = dx * dx + dy * dy;
-      if (r2 > rmax2) {
-        /* scale factor in float (IEEE sqrt and divide), applied in double */
-        const float sf = (float)prm->r_max / sqrtf((float)r2);
-        const double s = (double)sf;
-        px = ox + s * dx;
-        py = oy + s * dy;
+      const float dx = pxf - bg.oxf, dy = pyf - bg.oyf;
+      const float dx2 = dx * dx, dy2 = dy * dy;
+      const float r2 = dx2 + dy2;
+      if (r2 > bg.rmax2f) {
+        const float sf = bg.rmaxf / sqrtf(r2);
+        const float mx = sf * dx, my = sf * dy;
+        pxf = bg.oxf + mx;
+        pyf = bg.oyf + my;
         hit_ok = 0;
         flags |= GVO_F_RANGECAP;
       }
     }
     int32_t ex, ey;
-    if (!gvo_grid_get_index(g, px, py, &ex, &ey)) {
-      const double eax = gvo_index_coord_mul(px, g->len_x, g->pos_x, inv_res);
-      const double eay = gvo_index_coord_mul(py, g->len_y, g->pos_y, inv_res);
-      gvo_clip_end(oax, oay, eax, eay, g->nx, g->ny, &ex, &ey);
+    /* X1: cell = grid_map getIndex of the (float) base-frame position, promoted to double */
+    if (!gvo_grid_get_index(g, (double)pxf, (double)pyf, &ex, &ey)) {
+      gvo_clip_end(&bg, pxf, pyf, g->nx, g->ny, &ex, &ey);
       hit_ok = 0;
       flags |= GVO_F_CLIPPED;
     }

@@ -99,6 +99,85 @@ def test_fuse_generic_intrinsics(ctx, K):
     assert_bits_equal(uv[0, 1], ev, "v")
 
 
+def test_certified_float_projection_adversarial(ctx):
+    """Labels-only calls take the certified float path (fuse_point_fast).  Aim points within a
+    few ulps of every decision boundary — image edges, 32-px tile edges, box edges (integer and
+    fractional) — at many depths: the float path must either agree with the FP64 reference or
+    defer to it, so labels stay bit-exact."""
+    wl = synth.C1
+    set_camera(ctx, wl, T=False)
+    rng = np.random.default_rng(77)
+    boxes = synth.make_boxes(wl, n=60)
+    boxes["x_max"][::4] += 0.3
+    boxes["y_min"][::3] -= 0.7
+    edges_u = np.unique(np.concatenate([boxes["x_min"], boxes["x_max"], np.arange(0, 417, 32), [0, 416]]))
+    edges_v = np.unique(np.concatenate([boxes["y_min"], boxes["y_max"], np.arange(0, 417, 32), [0, 416]]))
+    X, Y, Z = [], [], []
+    for _ in range(40):
+        z = np.float32(rng.uniform(0.5, 80.0))
+        for eu in edges_u:
+            x0 = np.float32(z * (eu - 208.0) / 208.0)
+            xs = x0 + np.arange(-4, 5).astype(np.float32) * np.spacing(x0)
+            vv = rng.uniform(0, 416, xs.size)
+            X.append(xs); Y.append((z * (vv - 208.0) / 208.0).astype(np.float32)); Z.append(np.full(xs.size, z, np.float32))
+        for ev in edges_v:
+            y0 = np.float32(z * (ev - 208.0) / 208.0)
+            ys = y0 + np.arange(-4, 5).astype(np.float32) * np.spacing(y0)
+            uu = rng.uniform(0, 416, ys.size)
+            X.append((z * (uu - 208.0) / 208.0).astype(np.float32)); Y.append(ys); Z.append(np.full(ys.size, z, np.float32))
+    X, Y, Z = (np.concatenate(a) for a in (X, Y, Z))
+    # corners: both coordinates on an edge at once
+    cu, cv = rng.choice(edges_u, 4000), rng.choice(edges_v, 4000)
+    zc = rng.uniform(0.5, 80.0, 4000).astype(np.float32)
+    X = np.concatenate([X, (zc * (cu - 208.0) / 208.0).astype(np.float32)])
+    Y = np.concatenate([Y, (zc * (cv - 208.0) / 208.0).astype(np.float32)])
+    Z = np.concatenate([Z, zc])
+    lab_fast, _, _ = ctx.fuse(X, Y, Z, boxes, want_pix=False, want_uv=False)
+    lab_exact, _, _ = ctx.fuse(X, Y, Z, boxes)
+    elab, _, _, _ = orc.project_label(wl.K(), 416, 416, X, Y, Z, boxes)
+    assert np.array_equal(lab_exact[0], elab)
+    assert np.array_equal(lab_fast[0], elab)
+    assert X.size > 80000 and (elab >= 0).sum() > 20000 and (elab < 0).sum() > 20000
+    # huge / tiny magnitudes must leave the fast path gracefully
+    Xb = np.array([1e20, -1e20, 3e38, 1e-30, 0.0, 1e16], np.float32)
+    Yb = np.array([0.0, 1e20, 0.0, 1e-30, -1e19, 0.0], np.float32)
+    Zb = np.array([1e20, 1e20, 3e38, 1e-2, 1e19, 1e16], np.float32)
+    lf, _, _ = ctx.fuse(Xb, Yb, Zb, boxes, want_pix=False, want_uv=False)
+    le, _, _, _ = orc.project_label(wl.K(), 416, 416, Xb, Yb, Zb, boxes)
+    assert np.array_equal(lf[0], le)
+
+
+def test_certified_index_adversarial(ctx):
+    """Beams ending within a few ulps of cell and map boundaries: the fixed-point index must
+    agree with grid_map's double-precision getIndex or defer to it."""
+    for nx, ny, res, px, py in [(2048, 2048, 0.1, 0.0, 0.0), (500, 200, 0.1, 16.0, 0.0), (8192, 8192, 0.05, 3.3, -7.1)]:
+        g = orc.Grid.from_cells(nx, ny, res, px, py)
+        ctx.grid_init_cells(nx, ny, res, px, py)
+        T = np.eye(4, dtype=np.float32)
+        T[0, 3], T[1, 3] = px + 0.01, py - 0.02
+        ctx.set_base_transform(T)
+        rng = np.random.default_rng(nx)
+        i = rng.integers(-2, nx + 3, 30000)
+        j = rng.integers(-2, ny + 3, 30000)
+        # x of the boundary between cells i-1 and i: a = i  <=>  p = half + pos - i*res
+        bx = ((0.5 * g.len_x + px) - i * res).astype(np.float32)
+        by = ((0.5 * g.len_y + py) - j * res).astype(np.float32)
+        k = rng.integers(-3, 4, 30000)
+        bx = bx + k.astype(np.float32) * np.spacing(bx)
+        by_rand = rng.uniform(py - g.len_y / 2, py + g.len_y / 2, 30000).astype(np.float32)
+        bx_rand = rng.uniform(px - g.len_x / 2, px + g.len_x / 2, 30000).astype(np.float32)
+        X = np.concatenate([bx, bx_rand, bx])
+        Y = np.concatenate([by_rand, by + k.astype(np.float32) * np.spacing(by), by])
+        Z = np.zeros_like(X)
+        upd, ecells, eflags = g.accumulate(T, X, Y, Z)
+        cells, flags = ctx.grid_accumulate(X, Y, Z)
+        assert np.array_equal(cells, ecells), (nx, res)
+        assert np.array_equal(flags, eflags)
+        hit, miss = ctx.grid_counts()
+        assert np.array_equal(hit, g.hit) and np.array_equal(miss, g.miss)
+        assert (eflags & orc.F_CLIPPED).astype(bool).sum() > 50
+
+
 def test_fuse_empty_and_no_boxes(ctx):
     wl = synth.C1
     set_camera(ctx, wl)
