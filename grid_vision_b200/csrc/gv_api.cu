@@ -261,12 +261,14 @@ int note_beams(gv_ctx *ctx, unsigned long long n)
 int launch_points(gv_ctx *ctx, bool fuse, bool bin, PointArgs &a, unsigned ntiles, size_t smem)
 {
   if (ntiles == 0) return GV_OK;
-  const bool exact_uv = a.pix != nullptr || a.uv != nullptr;
+  const bool exact_uv = a.pix != nullptr || a.uv != nullptr || a.cell_out != nullptr ||
+                        a.flags_out != nullptr;
   if (fuse && bin) k_points<true, true, false, false><<<ntiles, kThreads, smem, ctx->stream>>>(a);
   else if (fuse && a.ncam > 1 && exact_uv) k_points<true, false, true, true><<<ntiles, kThreads, smem, ctx->stream>>>(a);
   else if (fuse && a.ncam > 1) k_points<true, false, true, false><<<ntiles, kThreads, smem, ctx->stream>>>(a);
   else if (fuse && exact_uv) k_points<true, false, false, true><<<ntiles, kThreads, smem, ctx->stream>>>(a);
   else if (fuse) k_points<true, false, false, false><<<ntiles, kThreads, smem, ctx->stream>>>(a);
+  else if (exact_uv) k_points<false, true, false, true><<<ntiles, kThreads, smem, ctx->stream>>>(a);
   else k_points<false, true, false, false><<<ntiles, kThreads, smem, ctx->stream>>>(a);
   GV_LAUNCH_CHECK();
   return GV_OK;
@@ -506,12 +508,15 @@ int refresh_origin(gv_ctx *ctx)
   // for every in-map p, i.e. (half + |pos|)/res < ~2^28; otherwise always the exact path
   b.c0xd = g.half_x + g.pos_x;
   b.c0yd = g.half_y + g.pos_y;
-  b.mres = 1048576.0 / g.res;
-  b.klim_x = (long long)g.nx << 20;
-  b.klim_y = (long long)g.ny << 20;
+  b.mres = 65536.0 / g.res;
+  b.klim_x = g.nx << 16;
+  b.klim_y = g.ny << 16;
   const double span = (g.half_x + std::fabs(g.pos_x) > g.half_y + std::fabs(g.pos_y)
                          ? g.half_x + std::fabs(g.pos_x) : g.half_y + std::fabs(g.pos_y)) / g.res;
-  b.fast_index_ok = span < 134217728.0 ? 1 : 0;
+  b.fast_index_ok = (span < 134217728.0 && g.nx <= 16384 && g.ny <= 16384) ? 1 : 0;
+  b.t_small = 1;
+  for (int i = 0; i < 12; ++i)
+    if (!(std::fabs(b.T[i]) < 1.0e6f)) b.t_small = 0;
   return GV_OK;
 }
 
@@ -692,6 +697,11 @@ int gv_set_cameras(gv_ctx *ctx, int ncam, const double *K, const float *T_cam_li
     d.Wf = (float)d.W;
     d.Hf = (float)d.H;
     d.canon = is_canonical_K(d.K) ? 1 : 0;
+    d.t_small = 1;
+    for (int i = 0; i < 12; ++i)
+      if (!(std::fabs(d.T[i]) < 1.0e6f)) d.t_small = 0;
+    for (int i = 0; i < 9; ++i)
+      if (!(std::fabs(d.K[i]) < 1.0e6)) d.canon = 0;  // fast float path needs sane intrinsics
     // certified float projection constants: E(q) = e6*|q| + e0 = 2^-22 (6|q| + |c| + 1)
     d.fxf = (float)d.K[0];
     d.fyf = (float)d.K[4];

@@ -34,6 +34,7 @@ struct CamDev {
   int has_T;     // 0: cloud already in the camera frame
   int canon;     // K == [fx 0 cx; 0 fy cy; 0 0 1] with float-representable entries
   int box_begin, box_end;
+  int t_small;   // every |T entry| < 1e6 (with small3 inputs the transform cannot overflow)
   // certified float projection (canonical K only): exact float copies of fx, fy, cx, cy and the
   // constants of the error bound E(q) = e6*|q| + e0 (see fuse_point_fast)
   float fxf, fyf, cxf, cyf;
@@ -55,10 +56,11 @@ struct BinDev {
   // float geometry of free-space-only beams (oracle gvo_beam_geom)
   float oxf, oyf, c0xf, c0yf, inv_resf, oaxf, oayf, rmaxf, rmax2f;
   int cap;
-  // certified fixed-point index: k = trunc((c0 - p) * (2^20 / res)) holds cell and fraction
+  // certified fixed-point index: k = trunc((c0 - p) * (2^16 / res)) holds cell and fraction
   double c0xd, c0yd, mres;
-  long long klim_x, klim_y;  // size << 20
+  int klim_x, klim_y;  // size << 16
   int fast_index_ok;
+  int t_small;
 };
 
 struct PointArgs {
@@ -105,6 +107,16 @@ __device__ __forceinline__ bool finitef(float v)
 __device__ __forceinline__ bool finite3(float x, float y, float z)
 {
   return finitef(x) && finitef(y) && finitef(z);
+}
+
+// all three |v| < 1e9 (hence finite): one integer max over the sign-stripped bit patterns, so
+// NaN and Inf (larger patterns) fail.  With |T entries| < 1e6 (t_small, checked on the host) the
+// SE(3) outputs are then below 3.1e15 in magnitude: finite, no separate test needed.
+__device__ __forceinline__ bool small3(float x, float y, float z)
+{
+  const unsigned ux = __float_as_uint(x) & 0x7fffffffu, uy = __float_as_uint(y) & 0x7fffffffu,
+                 uz = __float_as_uint(z) & 0x7fffffffu;
+  return max(max(ux, uy), uz) < 0x4e6e6b28u;  // bits of 1.0e9f
 }
 
 // R1: PCL Transformer<float>::se3 (SSE2): out = c0*x + (c1*y + (c2*z + c3)); call site
@@ -173,32 +185,30 @@ __device__ __forceinline__ bool grid_get_index(const GridGeom &g, double px, dou
 // Certified fast version of grid_get_index for float positions (X1).  The contract is
 //   inside  <=>  0 <= -((p - pos) - half) < len  (per axis, double)      [checkIfPositionWithinMap]
 //   index   =   trunc(-(((p - half) - pos) / res))                       [getIndexFromPosition]
-// Fast path: a' = (c0 - p) * (2^20/res) in double with c0 = RN(half + pos); k = trunc(a') is a
-// 44.20 fixed-point image of the exact index coordinate a.  a' / 2^20 differs from the
-// reference's rounded a (and q/res from a) by at most 8 * 2^-53 * (|p| + half + |pos|) / res,
-// which the host guarantees is below 2^-21 cells (fast_index_ok), so when the 20-bit fraction
-// of k lies in [16, 2^20 - 16] both formulas truncate to the same cell, and when
-// 16 <= k < (size << 20) - 16 the point is certainly inside.  Anything else (a point within
-// 1.5e-5 cells of a cell or map boundary, NaN, a huge coordinate) takes the exact path.
+// Fast path: a' = (c0 - p) * (2^16/res) in double with c0 = RN(half + pos); k = trunc(a') is a
+// 16.16 fixed-point image of the exact index coordinate a (the conversion saturates, NaN -> 0).
+// a' / 2^16 differs from the reference's rounded a (and q/res from a) by at most
+// 8 * 2^-53 * (|p| + half + |pos|) / res, which the host guarantees is below 2^-20 cells
+// (fast_index_ok, which also requires size <= 16384 so k fits), so when the 16-bit fraction of
+// k lies in [8, 2^16 - 8] both formulas truncate to the same cell, and when
+// 8 <= k < (size << 16) - 8 the point is certainly inside.  Anything else (a point within
+// 1.2e-4 cells of a cell or map boundary, NaN, a huge coordinate) takes the exact path.
 // Returns true with (ix,iy) when inside; false when outside.  Bit-identical by construction.
 __device__ __forceinline__ bool grid_get_index_cert(const BinDev &b, float pxf, float pyf, int &ix,
                                                     int &iy)
 {
   if (b.fast_index_ok) {
-    const long long kx = __double2ll_rz(__dmul_rn(__dsub_rn(b.c0xd, (double)pxf), b.mres));
-    const long long ky = __double2ll_rz(__dmul_rn(__dsub_rn(b.c0yd, (double)pyf), b.mres));
-    const unsigned fx = (unsigned)kx & 0xfffffu, fy = (unsigned)ky & 0xfffffu;
-    const bool frac_ok = (fx - 16u <= 0xfffffu - 32u) && (fy - 16u <= 0xfffffu - 32u);
-    if (frac_ok && kx >= 16 && ky >= 16 && kx < b.klim_x - 16 && ky < b.klim_y - 16) {
-      ix = (int)(kx >> 20);
-      iy = (int)(ky >> 20);
+    const int kx = __double2int_rz(__dmul_rn(__dsub_rn(b.c0xd, (double)pxf), b.mres));
+    const int ky = __double2int_rz(__dmul_rn(__dsub_rn(b.c0yd, (double)pyf), b.mres));
+    const unsigned fx = (unsigned)kx & 0xffffu, fy = (unsigned)ky & 0xffffu;
+    const bool frac_ok = (fx - 8u <= 0xffffu - 16u) && (fy - 8u <= 0xffffu - 16u);
+    if (frac_ok && kx >= 8 && ky >= 8 && kx < b.klim_x - 8 && ky < b.klim_y - 8) {
+      ix = kx >> 16;
+      iy = ky >> 16;
       return true;
     }
-    // certainly outside: more than 16/2^20 cells beyond an edge on some axis
-    if (kx < -16 || ky < -16 || kx >= b.klim_x + 16 || ky >= b.klim_y + 16) {
-      // (NaN converts to 0 and never lands here)
-      return false;
-    }
+    // certainly outside: more than 8/2^16 cells beyond an edge on some axis
+    if (kx < -8 || ky < -8 || kx >= b.klim_x + 8 || ky >= b.klim_y + 8) return false;
   }
   return grid_get_index(b.g, (double)pxf, (double)pyf, ix, iy);
 }
@@ -240,11 +250,14 @@ __device__ __forceinline__ void bin_point(const BinDev &b, float x, float y, flo
 {
   cell = -1;
   flags = 0;
-  if (!b.origin_ok) return;
-  if (!finite3(x, y, z)) return;
   float bx, by, bz;
-  se3(b.T, x, y, z, bx, by, bz);
-  if (!finite3(bx, by, bz)) return;
+  if (b.t_small && small3(x, y, z)) {
+    se3(b.T, x, y, z, bx, by, bz);  // cannot overflow: finite
+  } else {
+    if (!finite3(x, y, z)) return;
+    se3(b.T, x, y, z, bx, by, bz);
+    if (!finite3(bx, by, bz)) return;
+  }
   bool hit_ok = true;
   flags = 1u;  // GV_F_VALID
   if (b.cap) {
@@ -336,16 +349,22 @@ __device__ __forceinline__ int fuse_point(const CamDev &cam, int is_dense, float
   pix = -1;
   u = v = __int_as_float(0x7fc00000);
   float X = px, Y = py, Z = pz;
-  // R1 (pcl::transformPointCloud: non-finite points pass through when !is_dense)
-  if (cam.has_T && (is_dense || finite3(X, Y, Z))) se3(cam.T, px, py, pz, X, Y, Z);
-  // ref: src/cloud_detections.cpp:264
-  if (finite3(X, Y, Z) && !(Z <= 0.001f)) {
-    if (!EXACT_UV && cam.canon) {
-      // magnitudes the error analysis (and __fdividef) covers; anything larger goes exact
-      const float big = 1.0e15f;
-      if (fabsf(X) < big && fabsf(Y) < big && Z < big &&
-          fuse_point_fast(cam, X, Y, Z, s_box, nb, mset, shift, mtx, mwords, lab))
-        return lab;
+  bool ok;
+  const bool small = cam.t_small && small3(px, py, pz);
+  if (small) {
+    // finite in, |T| < 1e6: finite out (< 3.1e15), so ref :264 reduces to the depth test
+    if (cam.has_T) se3(cam.T, px, py, pz, X, Y, Z);
+    ok = Z > 0.001f;
+  } else {
+    // R1 (pcl::transformPointCloud: non-finite points pass through when !is_dense)
+    if (cam.has_T && (is_dense || finite3(X, Y, Z))) se3(cam.T, px, py, pz, X, Y, Z);
+    // ref: src/cloud_detections.cpp:264
+    ok = finite3(X, Y, Z) && !(Z <= 0.001f);
+  }
+  if (ok) {
+    if (!EXACT_UV && cam.canon && small) {
+      // magnitudes are inside what the error analysis (and __fdividef) covers
+      if (fuse_point_fast(cam, X, Y, Z, s_box, nb, mset, shift, mtx, mwords, lab)) return lab;
       lab = -1;
     }
     project_point(cam, X, Y, Z, u, v);
@@ -381,7 +400,9 @@ __device__ __forceinline__ int fuse_point(const CamDev &cam, int is_dense, float
 
 // MULTI = false: one camera (index 0, every parameter a compile-time constant-bank operand);
 // MULTI = true: loop over a.ncam cameras of a rig (BASELINE config 4).
-// EXACT_UV = true: u,v / pixel parity outputs requested, projection always in FP64.
+// EXACT_UV = true: a parity output (u,v / pixel / end cell / beam flags) is requested; the
+// projection then always runs in FP64 and the nullable parity pointers are honoured.  The
+// throughput instantiations (EXACT_UV = false) write labels and bin beams only.
 template <bool FUSE, bool BIN, bool MULTI, bool EXACT_UV>
 __global__ void __launch_bounds__(kThreads) k_points(const __grid_constant__ PointArgs a)
 {
@@ -421,11 +442,21 @@ __global__ void __launch_bounds__(kThreads) k_points(const __grid_constant__ Poi
 
   const float *xp = a.x + start, *yp = a.y + start, *zp = a.z + start;
   int16_t *lab_p = a.labels ? a.labels + start : nullptr;
-  int32_t *pix_p = a.pix ? a.pix + start : nullptr;
-  float *uv_p = a.uv ? a.uv + start : nullptr;
+  int32_t *pix_p = (EXACT_UV && a.pix) ? a.pix + start : nullptr;
+  float *uv_p = (EXACT_UV && a.uv) ? a.uv + start : nullptr;
   const int16_t *labin_p = (!FUSE && a.labels_in) ? a.labels_in + start : nullptr;
-  int32_t *cell_p = a.cell_out ? a.cell_out + start : nullptr;
-  uint8_t *flag_p = a.flags_out ? a.flags_out + start : nullptr;
+  int32_t *cell_p = (EXACT_UV && a.cell_out) ? a.cell_out + start : nullptr;
+  uint8_t *flag_p = (EXACT_UV && a.flags_out) ? a.flags_out + start : nullptr;
+  if (BIN && !a.bin.origin_ok) {
+    // sensor outside the map: every beam is dropped (parity outputs say so)
+    if (EXACT_UV)
+      for (unsigned k = threadIdx.x; k < cnt; k += kThreads) {
+        if (cell_p) cell_p[k] = -1;
+        if (flag_p) flag_p[k] = 0;
+      }
+    if (!FUSE) return;
+  }
+  const bool do_bin = BIN && a.bin.origin_ok;
   const int nb0 = a.nframes > 0 ? be - bb : a.cam[0].box_end - a.cam[0].box_begin;
 
   // One point per thread per pass, next pass prefetched.  (A 4-points-per-thread version with
@@ -486,7 +517,7 @@ __global__ void __launch_bounds__(kThreads) k_points(const __grid_constant__ Poi
       }
     }
 
-    if (BIN) {
+    if (BIN && do_bin) {
       int label = lab0;
       if (!FUSE && labin_p) label = labin_p[k];
       int cell;
@@ -494,8 +525,10 @@ __global__ void __launch_bounds__(kThreads) k_points(const __grid_constant__ Poi
       bin_point(a.bin, px, py, pz, label, cell, flags);
       // one 64-bit RED per beam: low word counts beams ending in the cell, high word hits
       if (cell >= 0) atomicAdd(a.ends + cell, (flags & 2u) ? 0x100000001ull : 1ull);
-      if (cell_p) cell_p[k] = cell;
-      if (flag_p) flag_p[k] = (uint8_t)flags;
+      if (EXACT_UV) {
+        if (cell_p) cell_p[k] = cell;
+        if (flag_p) flag_p[k] = (uint8_t)flags;
+      }
     }
     k = knext;
   }

@@ -261,6 +261,55 @@ def test_transform_points_R1(ctx):
             assert_bits_equal(g, e, f"dense={dense}")
 
 
+def _random_rigid(seed, t):
+    rng = np.random.default_rng(seed)
+    q = rng.normal(size=4)
+    q /= np.linalg.norm(q)
+    w, x, y, z = q
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                  [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                  [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    T = np.eye(4)
+    T[:3, :3] = R
+    T[:3, 3] = t
+    return T.astype(np.float32)
+
+
+def test_general_rotations_no_fma_contraction(ctx):
+    """SE(3) with irrational rotation entries for BOTH extrinsics: a fused multiply-add anywhere
+    in the transform would change low bits of u,v / end cells (0/+-1 matrices cannot show that)."""
+    wl = small(synth.C1, rings=64, azimuth=1024)
+    xyz = scan(wl)
+    boxes = synth.make_boxes(wl)
+    Tc = (synth.camera_extrinsics(1)[0].astype(np.float64) @ _random_rigid(1, [0.3, -0.2, 0.1]).astype(np.float64)).astype(np.float32)
+    Tc[3] = [0, 0, 0, 1]
+    ctx.set_cameras(wl.K().reshape(1, 9), [[wl.image_w, wl.image_h]], Tc.reshape(1, 16))
+    lab, pix, uv = ctx.fuse(*xyz, boxes)
+    elab, epix, eu, ev = oracle_fuse(wl, xyz, boxes, Tc)
+    assert np.array_equal(lab[0], elab) and np.array_equal(pix[0], epix)
+    assert_bits_equal(uv[0, 0], eu, "u")
+    assert_bits_equal(uv[0, 1], ev, "v")
+    got = ctx.transform_points(0, *xyz)
+    for g_, e_ in zip(got, orc.transform_points(Tc, *xyz)):
+        assert_bits_equal(g_, e_)
+    lab_fast, _, _ = ctx.fuse(*xyz, boxes, want_pix=False, want_uv=False)
+    assert np.array_equal(lab_fast[0], elab)
+    # base transform: yaw/pitch/roll + offset
+    Tb = _random_rigid(2, [1.7, -0.6, 2.4])
+    Tb[:3, :3] = (0.97 * np.eye(3) + 0.03 * Tb[:3, :3]).astype(np.float32)  # keep the scan roughly level
+    g = oracle_grid(wl)
+    ctx.grid_init_cells(wl.grid_nx, wl.grid_ny, wl.resolution)
+    ctx.set_base_transform(Tb)
+    upd, ecells, eflags = g.accumulate(Tb, *xyz, r_max=9.0)
+    cells, flags = ctx.grid_accumulate(*xyz, None, gv.accum_params(r_max=9.0))
+    assert np.array_equal(cells, ecells) and np.array_equal(flags, eflags)
+    hit, miss = ctx.grid_counts()
+    assert np.array_equal(hit, g.hit) and np.array_equal(miss, g.miss)
+    cells2, _ = ctx.grid_accumulate(*xyz, None, gv.accum_params(r_max=9.0), want_cells=False)
+    hit2, miss2 = ctx.grid_counts()
+    assert np.array_equal(hit2, 2 * g.hit) and np.array_equal(miss2, 2 * g.miss)  # throughput instance
+
+
 def test_project_kdtree_R4(ctx):
     wl = synth.C1
     xyz = scan(small(wl, rings=32, azimuth=2048))
