@@ -263,13 +263,17 @@ int launch_points(gv_ctx *ctx, bool fuse, bool bin, PointArgs &a, unsigned ntile
   if (ntiles == 0) return GV_OK;
   const bool exact_uv = a.pix != nullptr || a.uv != nullptr || a.cell_out != nullptr ||
                         a.flags_out != nullptr;
-  if (fuse && bin) k_points<true, true, false, false><<<ntiles, kThreads, smem, ctx->stream>>>(a);
-  else if (fuse && a.ncam > 1 && exact_uv) k_points<true, false, true, true><<<ntiles, kThreads, smem, ctx->stream>>>(a);
-  else if (fuse && a.ncam > 1) k_points<true, false, true, false><<<ntiles, kThreads, smem, ctx->stream>>>(a);
-  else if (fuse && exact_uv) k_points<true, false, false, true><<<ntiles, kThreads, smem, ctx->stream>>>(a);
-  else if (fuse) k_points<true, false, false, false><<<ntiles, kThreads, smem, ctx->stream>>>(a);
-  else if (exact_uv) k_points<false, true, false, true><<<ntiles, kThreads, smem, ctx->stream>>>(a);
-  else k_points<false, true, false, false><<<ntiles, kThreads, smem, ctx->stream>>>(a);
+  // COMMON: flags the specialised hot loop assumes (see k_points); checked here, once
+  const bool common = fuse && bin && a.ncam == 1 && a.cam[0].has_T && a.cam[0].t_small &&
+                      a.cam[0].canon && a.bin.t_small && a.bin.fast_index_ok && a.mask_words == 1;
+  if (fuse && bin && common) k_points<true, true, false, false, true><<<ntiles, kThreads, smem, ctx->stream>>>(a);
+  else if (fuse && bin) k_points<true, true, false, false, false><<<ntiles, kThreads, smem, ctx->stream>>>(a);
+  else if (fuse && a.ncam > 1 && exact_uv) k_points<true, false, true, true, false><<<ntiles, kThreads, smem, ctx->stream>>>(a);
+  else if (fuse && a.ncam > 1) k_points<true, false, true, false, false><<<ntiles, kThreads, smem, ctx->stream>>>(a);
+  else if (fuse && exact_uv) k_points<true, false, false, true, false><<<ntiles, kThreads, smem, ctx->stream>>>(a);
+  else if (fuse) k_points<true, false, false, false, false><<<ntiles, kThreads, smem, ctx->stream>>>(a);
+  else if (exact_uv) k_points<false, true, false, true, false><<<ntiles, kThreads, smem, ctx->stream>>>(a);
+  else k_points<false, true, false, false, false><<<ntiles, kThreads, smem, ctx->stream>>>(a);
   GV_LAUNCH_CHECK();
   return GV_OK;
 }
@@ -350,13 +354,13 @@ int fuse_dev_impl(gv_ctx *ctx, const float *d_x, const float *d_y, const float *
   const size_t smem = (size_t)a.smem_boxes * sizeof(float4) +
                       (size_t)ctx->ncam * a.mask_stride * sizeof(unsigned long long);
   if (smem > 48 * 1024) {
-    GV_CUDA(cudaFuncSetAttribute(k_points<true, false, false, false>,
+    GV_CUDA(cudaFuncSetAttribute(k_points<true, false, false, false, false>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GV_CUDA(cudaFuncSetAttribute(k_points<true, false, false, true>,
+    GV_CUDA(cudaFuncSetAttribute(k_points<true, false, false, true, false>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GV_CUDA(cudaFuncSetAttribute(k_points<true, false, true, false>,
+    GV_CUDA(cudaFuncSetAttribute(k_points<true, false, true, false, false>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GV_CUDA(cudaFuncSetAttribute(k_points<true, false, true, true>,
+    GV_CUDA(cudaFuncSetAttribute(k_points<true, false, true, true, false>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   return launch_points(ctx, true, false, a, blocks_for(n, a.tile_pts), smem);
@@ -1252,7 +1256,7 @@ static int process_batch_impl(gv_ctx *ctx, const float *px, const float *py, con
   const size_t smem = (size_t)max_boxes * sizeof(float4) +
                       (size_t)a.mask_stride * sizeof(unsigned long long);
   if (smem > 48 * 1024)
-    GV_CUDA(cudaFuncSetAttribute(k_points<true, true, false, false>,
+    GV_CUDA(cudaFuncSetAttribute(k_points<true, true, false, false, false>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
   if (points_on_device) {

@@ -194,10 +194,11 @@ __device__ __forceinline__ bool grid_get_index(const GridGeom &g, double px, dou
 // 8 <= k < (size << 16) - 8 the point is certainly inside.  Anything else (a point within
 // 1.2e-4 cells of a cell or map boundary, NaN, a huge coordinate) takes the exact path.
 // Returns true with (ix,iy) when inside; false when outside.  Bit-identical by construction.
+template <bool COMMON>
 __device__ __forceinline__ bool grid_get_index_cert(const BinDev &b, float pxf, float pyf, int &ix,
                                                     int &iy)
 {
-  if (b.fast_index_ok) {
+  if (COMMON || b.fast_index_ok) {
     const int kx = __double2int_rz(__dmul_rn(__dsub_rn(b.c0xd, (double)pxf), b.mres));
     const int ky = __double2int_rz(__dmul_rn(__dsub_rn(b.c0yd, (double)pyf), b.mres));
     const unsigned fx = (unsigned)kx & 0xffffu, fy = (unsigned)ky & 0xffffu;
@@ -245,13 +246,15 @@ __device__ __forceinline__ void clip_end(const BinDev &b, float pxf, float pyf, 
 }
 
 // X1: one beam -> (end cell, flags).  Mirrors the per-point body of oracle gvo_accumulate.
+// COMMON: t_small and fast_index_ok are known true at compile time (host-checked).
+template <bool COMMON>
 __device__ __forceinline__ void bin_point(const BinDev &b, float x, float y, float z, int label,
                                           int &cell, unsigned &flags)
 {
   cell = -1;
   flags = 0;
   float bx, by, bz;
-  if (b.t_small && small3(x, y, z)) {
+  if ((COMMON || b.t_small) && small3(x, y, z)) {
     se3(b.T, x, y, z, bx, by, bz);  // cannot overflow: finite
   } else {
     if (!finite3(x, y, z)) return;
@@ -272,14 +275,15 @@ __device__ __forceinline__ void bin_point(const BinDev &b, float x, float y, flo
     }
   }
   int ex, ey;
-  if (!grid_get_index_cert(b, bx, by, ex, ey)) {
+  if (!grid_get_index_cert<COMMON>(b, bx, by, ex, ey)) {
     clip_end(b, bx, by, ex, ey);
     hit_ok = false;
     flags |= 4u;  // GV_F_CLIPPED
   }
-  if (hit_ok && b.use_z_gate && !(bz >= b.z_min && bz <= b.z_max)) hit_ok = false;
-  if (hit_ok && b.occ_mode == 1 && !(label >= 0)) hit_ok = false;
-  if (hit_ok) flags |= 2u;  // GV_F_HIT
+  // branch-free hit predicate (z gate, labelled-only mode)
+  hit_ok = hit_ok & (!b.use_z_gate | ((bz >= b.z_min) & (bz <= b.z_max))) &
+           ((b.occ_mode != 1) | (label >= 0));
+  flags |= hit_ok ? 2u : 0u;  // GV_F_HIT
   cell = ex + ey * b.g.nx;
 }
 
@@ -339,7 +343,8 @@ __device__ __forceinline__ bool fuse_point_fast(const CamDev &cam, float X, floa
 
 // R1 + R3 for one point against one camera: returns the label (index local to the camera's /
 // frame's box list, -1 = none); pix/u/v are the parity outputs (EXACT_UV: always the FP64 path).
-template <bool EXACT_UV>
+// COMMON: has_T, t_small, canon and mwords == 1 are known true at compile time (host-checked).
+template <bool EXACT_UV, bool COMMON>
 __device__ __forceinline__ int fuse_point(const CamDev &cam, int is_dense, float px, float py,
                                           float pz, const float4 *s_box, int nb,
                                           const unsigned long long *mset, int shift, int mtx,
@@ -350,10 +355,10 @@ __device__ __forceinline__ int fuse_point(const CamDev &cam, int is_dense, float
   u = v = __int_as_float(0x7fc00000);
   float X = px, Y = py, Z = pz;
   bool ok;
-  const bool small = cam.t_small && small3(px, py, pz);
+  const bool small = (COMMON || cam.t_small) && small3(px, py, pz);
   if (small) {
     // finite in, |T| < 1e6: finite out (< 3.1e15), so ref :264 reduces to the depth test
-    if (cam.has_T) se3(cam.T, px, py, pz, X, Y, Z);
+    if (COMMON || cam.has_T) se3(cam.T, px, py, pz, X, Y, Z);
     ok = Z > 0.001f;
   } else {
     // R1 (pcl::transformPointCloud: non-finite points pass through when !is_dense)
@@ -362,9 +367,10 @@ __device__ __forceinline__ int fuse_point(const CamDev &cam, int is_dense, float
     ok = finite3(X, Y, Z) && !(Z <= 0.001f);
   }
   if (ok) {
-    if (!EXACT_UV && cam.canon && small) {
+    if (!EXACT_UV && (COMMON || cam.canon) && small) {
       // magnitudes are inside what the error analysis (and __fdividef) covers
-      if (fuse_point_fast(cam, X, Y, Z, s_box, nb, mset, shift, mtx, mwords, lab)) return lab;
+      if (fuse_point_fast(cam, X, Y, Z, s_box, nb, mset, shift, mtx, COMMON ? 1 : mwords, lab))
+        return lab;
       lab = -1;
     }
     project_point(cam, X, Y, Z, u, v);
@@ -403,7 +409,10 @@ __device__ __forceinline__ int fuse_point(const CamDev &cam, int is_dense, float
 // EXACT_UV = true: a parity output (u,v / pixel / end cell / beam flags) is requested; the
 // projection then always runs in FP64 and the nullable parity pointers are honoured.  The
 // throughput instantiations (EXACT_UV = false) write labels and bin beams only.
-template <bool FUSE, bool BIN, bool MULTI, bool EXACT_UV>
+// COMMON = true: the usual configuration (extrinsic present, sane magnitudes, canonical K,
+// certified index usable, <= 64 boxes per set) is fixed at compile time, which removes a dozen
+// uniform-flag branches from the hot loop; the host selects it, anything else runs COMMON = false.
+template <bool FUSE, bool BIN, bool MULTI, bool EXACT_UV, bool COMMON>
 __global__ void __launch_bounds__(kThreads) k_points(const __grid_constant__ PointArgs a)
 {
   extern __shared__ float4 s_dyn[];
@@ -440,58 +449,71 @@ __global__ void __launch_bounds__(kThreads) k_points(const __grid_constant__ Poi
     __syncthreads();
   }
 
-  const float *xp = a.x + start, *yp = a.y + start, *zp = a.z + start;
-  int16_t *lab_p = a.labels ? a.labels + start : nullptr;
-  int32_t *pix_p = (EXACT_UV && a.pix) ? a.pix + start : nullptr;
-  float *uv_p = (EXACT_UV && a.uv) ? a.uv + start : nullptr;
-  const int16_t *labin_p = (!FUSE && a.labels_in) ? a.labels_in + start : nullptr;
-  int32_t *cell_p = (EXACT_UV && a.cell_out) ? a.cell_out + start : nullptr;
-  uint8_t *flag_p = (EXACT_UV && a.flags_out) ? a.flags_out + start : nullptr;
+  // per-thread pointers that advance by one pass (256 points) per iteration
+  const unsigned long long t0 = start + threadIdx.x;
+  const float *xp = a.x + t0, *yp = a.y + t0, *zp = a.z + t0;
+  int16_t *lab_p = a.labels ? a.labels + t0 : nullptr;
+  int32_t *pix_p = (EXACT_UV && a.pix) ? a.pix + t0 : nullptr;
+  float *uv_p = (EXACT_UV && a.uv) ? a.uv + t0 : nullptr;
+  const int16_t *labin_p = (!FUSE && a.labels_in) ? a.labels_in + t0 : nullptr;
+  int32_t *cell_p = (EXACT_UV && a.cell_out) ? a.cell_out + t0 : nullptr;
+  uint8_t *flag_p = (EXACT_UV && a.flags_out) ? a.flags_out + t0 : nullptr;
   if (BIN && !a.bin.origin_ok) {
     // sensor outside the map: every beam is dropped (parity outputs say so)
     if (EXACT_UV)
       for (unsigned k = threadIdx.x; k < cnt; k += kThreads) {
-        if (cell_p) cell_p[k] = -1;
-        if (flag_p) flag_p[k] = 0;
+        if (cell_p) cell_p[k - threadIdx.x] = -1;
+        if (flag_p) flag_p[k - threadIdx.x] = 0;
       }
     if (!FUSE) return;
   }
   const bool do_bin = BIN && a.bin.origin_ok;
   const int nb0 = a.nframes > 0 ? be - bb : a.cam[0].box_end - a.cam[0].box_begin;
+  const float4 *box0 = s_box + (a.nframes > 0 ? 0 : a.cam[0].box_begin);
 
   // One point per thread per pass, next pass prefetched.  (A 4-points-per-thread version with
   // 128-bit loads ran out of instruction cache: 3.4k SASS instructions, 41% no-instruction
   // stalls in ncu; the path is issue-bound, not load-bound, so scalar coalesced loads win.)
-  unsigned k = threadIdx.x;
+  int left = (int)cnt - (int)threadIdx.x;  // points this thread still has to do: every kThreads-th
   float nx = 0.0f, ny = 0.0f, nz = 0.0f;
-  if (k < cnt) {
-    nx = __ldg(xp + k);
-    ny = __ldg(yp + k);
-    nz = __ldg(zp + k);
+  if (left > 0) {
+    nx = __ldg(xp);
+    ny = __ldg(yp);
+    nz = __ldg(zp);
   }
 #pragma unroll 1
-  while (k < cnt) {
+  while (left > 0) {
     const float px = nx, py = ny, pz = nz;
-    const unsigned knext = k + kThreads;
-    if (knext < cnt) {
-      nx = __ldg(xp + knext);
-      ny = __ldg(yp + knext);
-      nz = __ldg(zp + knext);
+    left -= kThreads;
+    if (left > 0) {
+      nx = __ldg(xp + kThreads);
+      ny = __ldg(yp + kThreads);
+      nz = __ldg(zp + kThreads);
     }
+    xp += kThreads;
+    yp += kThreads;
+    zp += kThreads;
     int lab0 = -1;
 
     if (FUSE) {
       if (!MULTI) {
         int pix;
         float u, v;
-        lab0 = fuse_point<EXACT_UV>(a.cam[0], a.is_dense, px, py, pz, s_box + (a.nframes > 0 ? 0 : a.cam[0].box_begin),
-                          nb0, s_mask, a.mask_shift[0], a.mask_tx[0], a.mask_words, pix, u, v);
-        if (lab_p) lab_p[k] = (int16_t)lab0;
+        lab0 = fuse_point<EXACT_UV, COMMON>(a.cam[0], a.is_dense, px, py, pz, box0, nb0, s_mask,
+                                            a.mask_shift[0], a.mask_tx[0], a.mask_words, pix, u, v);
+        if (lab_p) {
+          *lab_p = (int16_t)lab0;
+          lab_p += kThreads;
+        }
         if (EXACT_UV) {
-          if (pix_p) pix_p[k] = pix;
+          if (pix_p) {
+            *pix_p = pix;
+            pix_p += kThreads;
+          }
           if (uv_p) {
-            uv_p[k] = u;
-            uv_p[a.n + k] = v;
+            uv_p[0] = u;
+            uv_p[a.n] = v;
+            uv_p += kThreads;
           }
         }
       } else {
@@ -500,37 +522,51 @@ __global__ void __launch_bounds__(kThreads) k_points(const __grid_constant__ Poi
           const CamDev &cam = a.cam[c];
           int pix;
           float u, v;
-          const int lab = fuse_point<EXACT_UV>(cam, a.is_dense, px, py, pz, s_box + cam.box_begin,
-                                     cam.box_end - cam.box_begin, s_mask + c * a.mask_stride,
-                                     a.mask_shift[c], a.mask_tx[c], a.mask_words, pix, u, v);
+          const int lab = fuse_point<EXACT_UV, false>(cam, a.is_dense, px, py, pz, s_box + cam.box_begin,
+                                                      cam.box_end - cam.box_begin,
+                                                      s_mask + c * a.mask_stride, a.mask_shift[c],
+                                                      a.mask_tx[c], a.mask_words, pix, u, v);
           if (c == 0) lab0 = lab;
           const unsigned long long plane = (unsigned long long)c * a.n;
-          if (lab_p) lab_p[plane + k] = (int16_t)lab;
+          if (lab_p) lab_p[plane] = (int16_t)lab;
           if (EXACT_UV) {
-            if (pix_p) pix_p[plane + k] = pix;
+            if (pix_p) pix_p[plane] = pix;
             if (uv_p) {
-              uv_p[2 * plane + k] = u;
-              uv_p[2 * plane + a.n + k] = v;
+              uv_p[2 * plane] = u;
+              uv_p[2 * plane + a.n] = v;
             }
           }
+        }
+        if (lab_p) lab_p += kThreads;
+        if (EXACT_UV) {
+          if (pix_p) pix_p += kThreads;
+          if (uv_p) uv_p += kThreads;
         }
       }
     }
 
     if (BIN && do_bin) {
       int label = lab0;
-      if (!FUSE && labin_p) label = labin_p[k];
+      if (!FUSE && labin_p) {
+        label = *labin_p;
+        labin_p += kThreads;
+      }
       int cell;
       unsigned flags;
-      bin_point(a.bin, px, py, pz, label, cell, flags);
+      bin_point<COMMON>(a.bin, px, py, pz, label, cell, flags);
       // one 64-bit RED per beam: low word counts beams ending in the cell, high word hits
       if (cell >= 0) atomicAdd(a.ends + cell, (flags & 2u) ? 0x100000001ull : 1ull);
       if (EXACT_UV) {
-        if (cell_p) cell_p[k] = cell;
-        if (flag_p) flag_p[k] = (uint8_t)flags;
+        if (cell_p) {
+          *cell_p = cell;
+          cell_p += kThreads;
+        }
+        if (flag_p) {
+          *flag_p = (uint8_t)flags;
+          flag_p += kThreads;
+        }
       }
     }
-    k = knext;
   }
 }
 
