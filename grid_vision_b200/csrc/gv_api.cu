@@ -31,7 +31,7 @@ enum {
   S_X, S_Y, S_Z, S_AOS, S_LAB, S_PIX, S_UV, S_BOX_RAW, S_BOX_F4, S_FRAME_OFF, S_BOX_OFF,
   S_TILE_PREFIX, S_TILE_START, S_TILE_END, S_TILE_BOX, S_CELL, S_FLAGS, S_FOOT_IN, S_FOOT_LAB,
   S_RECT, S_SMALL, S_OX, S_OY, S_OZ, S_SCAN0, S_SCAN1, S_SCAN2, S_SCAN3, S_UVZ, S_INDICES,
-  S_LABELS_IN, S_MASKS, S_SET_OFF, S_COUNT
+  S_LABELS_IN, S_MASKS, S_SET_OFF, S_SWEEP, S_SWEEP_PREFIX, S_COUNT
 };
 
 constexpr size_t kPlanePad = 4096;  // slack cells so multi-GPU slabs can be equal-sized
@@ -56,8 +56,11 @@ struct gv_ctx {
   float *d_lo = nullptr, *d_occ = nullptr;
   int32_t *d_hit = nullptr, *d_miss = nullptr;
   unsigned long long *d_ends = nullptr;
-  uint2 *d_list = nullptr;
-  unsigned *d_list_count = nullptr;
+  unsigned *d_list_count = nullptr;  // work-item counter of the raycast sweep
+  SweepEntry *d_sweep = nullptr;     // sweep table for the current start cell
+  unsigned *d_sweep_prefix = nullptr;
+  int n_sweep = 0;
+  unsigned n_sweep_items = 0;
   bool counts_dirty = false, ends_dirty = false;
 
   bool has_base = false;
@@ -387,18 +390,76 @@ int accumulate_dev_impl(gv_ctx *ctx, const float *d_x, const float *d_y, const f
 int raycast_flush_impl(gv_ctx *ctx, unsigned rank, unsigned world)
 {
   if (!ctx->ends_dirty) return GV_OK;
+  ctx->ends_dirty = false;
+  if (!ctx->bin.origin_ok || ctx->n_sweep_items == 0) return GV_OK;  // nothing was binned
   GV_CUDA(cudaMemsetAsync(ctx->d_list_count, 0, sizeof(unsigned), ctx->stream));
   const unsigned nb = (unsigned)ctx->num_sms * 8u;
-  k_ends_compact<<<nb, kThreads, 0, ctx->stream>>>(ctx->d_ends, ctx->ncells, ctx->d_hit,
-                                                   ctx->d_miss, ctx->d_list, ctx->d_list_count,
-                                                   rank, world, ctx->d_stats);
+  k_raycast_sweep<<<nb, kThreads, 0, ctx->stream>>>(ctx->d_ends, ctx->d_hit, ctx->d_miss, ctx->d_sweep,
+                                                    ctx->d_sweep_prefix, ctx->n_sweep,
+                                                    ctx->n_sweep_items, ctx->bin.sx, ctx->bin.sy,
+                                                    ctx->g.nx, rank, world, ctx->d_list_count,
+                                                    ctx->d_stats);
   GV_LAUNCH_CHECK();
-  k_raycast_lines<<<nb, kThreads, 0, ctx->stream>>>(ctx->d_list, ctx->d_list_count, ctx->bin.sx,
-                                                    ctx->bin.sy, ctx->g.nx, ctx->d_miss,
-                                                    ctx->d_stats + 1);
-  GV_LAUNCH_CHECK();
-  ctx->ends_dirty = false;
+  // multi-GPU: this rank settled and cleared only the end cells of its own work items; the
+  // entries owned by the other ranks were handled there, drop them
+  if (world > 1)
+    GV_CUDA(cudaMemsetAsync(ctx->d_ends, 0, ctx->ncells * sizeof(unsigned long long), ctx->stream));
   ctx->counts_dirty = true;
+  return GV_OK;
+}
+
+// Sweep table for start cell (sx,sy): one entry per (direction, distance) with a non-empty
+// clipped segment, longest distance first; item_prefix counts 32-cell work items.
+int build_sweep_table(gv_ctx *ctx)
+{
+  ctx->n_sweep = 0;
+  ctx->n_sweep_items = 0;
+  if (!ctx->bin.origin_ok) return GV_OK;
+  const int nx = ctx->g.nx, ny = ctx->g.ny, sx = ctx->bin.sx, sy = ctx->bin.sy;
+  const int maxD = (nx > ny ? nx : ny);
+  std::vector<SweepEntry> ent;
+  ent.reserve(4 * (size_t)maxD + 1);
+  for (int D = maxD; D >= 1; --D) {
+    for (int dir = 0; dir < 4; ++dir) {
+      SweepEntry e;
+      e.dir = dir;
+      e.D = D;
+      if (dir < 2) {  // x-major: column sx +- D, |dy| <= D
+        const int x = dir == 0 ? sx + D : sx - D;
+        if (x < 0 || x >= nx) continue;
+        e.m0 = sy - D < 0 ? 0 : sy - D;
+        e.m1 = sy + D > ny - 1 ? ny - 1 : sy + D;
+      } else {  // y-major: row sy +- D, |dx| < D
+        const int y = dir == 2 ? sy + D : sy - D;
+        if (y < 0 || y >= ny) continue;
+        e.m0 = sx - (D - 1) < 0 ? 0 : sx - (D - 1);
+        e.m1 = sx + (D - 1) > nx - 1 ? nx - 1 : sx + (D - 1);
+      }
+      if (e.m1 < e.m0) continue;
+      ent.push_back(e);
+    }
+  }
+  ent.push_back(SweepEntry{4, 0, 0, 0});  // the start cell itself (zero-length beams)
+  std::vector<unsigned> prefix(ent.size() + 1);
+  unsigned long long items = 0;
+  for (size_t i = 0; i < ent.size(); ++i) {
+    prefix[i] = (unsigned)items;
+    items += (unsigned long long)(ent[i].m1 - ent[i].m0) / 32ull + 1ull;
+  }
+  GV_REQUIRE(items < 4294967295ull, GV_ERR_INVALID, "sweep table too large");
+  prefix[ent.size()] = (unsigned)items;
+  void *p = nullptr;
+  GV_TRY(reserve(ctx, S_SWEEP, ent.size() * sizeof(SweepEntry), &p));
+  ctx->d_sweep = static_cast<SweepEntry *>(p);
+  GV_TRY(reserve(ctx, S_SWEEP_PREFIX, prefix.size() * sizeof(unsigned), &p));
+  ctx->d_sweep_prefix = static_cast<unsigned *>(p);
+  GV_CUDA(cudaMemcpyAsync(ctx->d_sweep, ent.data(), ent.size() * sizeof(SweepEntry),
+                          cudaMemcpyHostToDevice, ctx->stream));
+  GV_CUDA(cudaMemcpyAsync(ctx->d_sweep_prefix, prefix.data(), prefix.size() * sizeof(unsigned),
+                          cudaMemcpyHostToDevice, ctx->stream));
+  GV_CUDA(cudaStreamSynchronize(ctx->stream));  // host vectors die here
+  ctx->n_sweep = (int)ent.size();
+  ctx->n_sweep_items = (unsigned)items;
   return GV_OK;
 }
 
@@ -472,11 +533,9 @@ void free_grid(gv_ctx *ctx)
   cudaFree(ctx->d_hit);
   cudaFree(ctx->d_miss);
   cudaFree(ctx->d_ends);
-  cudaFree(ctx->d_list);
   ctx->d_lo = ctx->d_occ = nullptr;
   ctx->d_hit = ctx->d_miss = nullptr;
   ctx->d_ends = nullptr;
-  ctx->d_list = nullptr;
   ctx->has_grid = false;
 }
 
@@ -521,7 +580,7 @@ int refresh_origin(gv_ctx *ctx)
   b.t_small = 1;
   for (int i = 0; i < 12; ++i)
     if (!(std::fabs(b.T[i]) < 1.0e6f)) b.t_small = 0;
-  return GV_OK;
+  return build_sweep_table(ctx);
 }
 
 int grid_init_impl(gv_ctx *ctx, double length_x, double length_y, double res, double pos_x,
@@ -552,7 +611,6 @@ int grid_init_impl(gv_ctx *ctx, double length_x, double length_y, double res, do
   GV_CUDA(cudaMalloc(&ctx->d_hit, padded * sizeof(int32_t)));
   GV_CUDA(cudaMalloc(&ctx->d_miss, padded * sizeof(int32_t)));
   GV_CUDA(cudaMalloc(&ctx->d_ends, padded * sizeof(unsigned long long)));
-  GV_CUDA(cudaMalloc(&ctx->d_list, ctx->ncells * sizeof(uint2)));
   ctx->has_grid = true;
   GV_CUDA(cudaMemsetAsync(ctx->d_lo, 0, padded * sizeof(float), ctx->stream));
   GV_CUDA(cudaMemsetAsync(ctx->d_occ, 0, padded * sizeof(float), ctx->stream));

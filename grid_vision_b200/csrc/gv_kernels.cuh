@@ -807,121 +807,129 @@ __global__ void __launch_bounds__(kThreads) k_label_scatter(const int16_t *__res
 }
 
 // ----------------------------------------------------------------------------------
-// K3: de-duplicated raycast.  All beams binned since the last flush share one start
-// cell, and a Bresenham line is a pure function of (start, end), so the traversed-cell
-// multiset of the whole batch is  sum over distinct end cells e of  w_e * line(start, e).
-//   pass A  compact the non-zero entries of the ends plane into a list, settle the end
-//           cells themselves (hit += high word, miss += low - high), clear the plane
-//   pass B  walk each listed line once, adding w_e to every cell before the end
+// K3: de-duplicated raycast as a distance-ordered sweep.
+// All beams binned since the last flush share one start cell s, and a Bresenham line is a pure
+// function of (start, end), so the traversed-cell multiset of the whole batch is
+//   sum over distinct end cells e of  w_e * line(s, e)           (exact: integer sums commute).
+// Work item = up to 32 end cells that lie side by side at the same major-axis distance D from s
+// (a piece of the column x = sx +- D for x-major lines, |dy| <= D; of the row y = sy +- D for
+// y-major lines, |dx| < D — the grid_map LineIterator's own case split).  One warp walks the
+// 32 lines of an item in lock step:
+//   * all 32 lines have exactly D + 1 cells: no divergence, no tail;
+//   * at step k every lane is at the same major coordinate and the minor coordinates are
+//     monotone in the lane index, so equal cells form contiguous lane runs: one shuffle + one
+//     ballot find the runs, and the run's weight is a difference of the warp prefix sum of w_e
+//     (computed once, the weights do not change along the walk): ONE RED per distinct cell;
+//   * lanes without beams carry weight 0 and ride along; an item with no beams is skipped.
+// Items are sorted by decreasing D and handed out through an atomic counter (longest first).
+// The end cells themselves are settled here too (hit += high word, miss += low - high) and the
+// ends plane is cleared.  Multi-GPU: item i belongs to rank i % world (the table is identical
+// on every rank).
+// grid_map LineIterator restatement: oracle gvo_line_init / gvo_line_step.
 // ----------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) k_ends_compact(unsigned long long *__restrict__ ends,
-                                                           unsigned long long ncells,
-                                                           int32_t *__restrict__ hit,
-                                                           int32_t *__restrict__ miss,
-                                                           uint2 *__restrict__ list,
-                                                           unsigned *__restrict__ list_count,
-                                                           unsigned rank, unsigned world,
-                                                           unsigned long long *__restrict__ stat_beams)
-{
-  const unsigned lane = threadIdx.x & 31;
-  unsigned long long beams = 0;
-  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-  // all lanes of a warp iterate together (bound rounded up to a warp multiple)
-  const unsigned long long nround = (ncells + 31ull) & ~31ull;
-  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nround;
-       i += stride) {
-    unsigned long long e = i < ncells ? ends[i] : 0ull;
-    if (e != 0ull) ends[i] = 0ull;
-    if (world == 1u || (unsigned)(i % world) == rank) beams += e & 0xffffffffull;
-    // multi-GPU (gv_grid_finalize_multi): every rank holds the all-reduced plane and owns
-    // the end cells with lin % world == rank; ownership by CELL, not by list position,
-    // because the append order below differs from rank to rank.
-    const bool nz = e != 0ull && (world == 1u || (unsigned)(i % world) == rank);
-    const unsigned m = __ballot_sync(0xffffffffu, nz);
-    if (m == 0) continue;
-    unsigned base = 0;
-    if (lane == 0) base = atomicAdd(list_count, (unsigned)__popc(m));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (nz) {
-      const unsigned total = (unsigned)(e & 0xffffffffull);
-      const unsigned hits = (unsigned)(e >> 32);
-      list[base + __popc(m & ((1u << lane) - 1u))] = make_uint2((unsigned)i, total);
-      if (hits) hit[i] += (int32_t)hits;
-      if (total - hits) miss[i] += (int32_t)(total - hits);
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) beams += __shfl_xor_sync(0xffffffffu, beams, o);
-  if (lane == 0 && beams) atomicAdd(stat_beams, beams);
-}
-
-// grid_map LineIterator restatement (oracle gvo_line_init / gvo_line_step)
-struct Line {
-  int x, y, inc1x, inc1y, inc2x, inc2y, den, num, add, n;
+struct SweepEntry {
+  int dir;  // 0: x = sx + D, 1: x = sx - D (x-major); 2: y = sy + D, 3: y = sy - D (y-major); 4: origin
+  int D;
+  int m0, m1;  // inclusive range of the minor coordinate (absolute index), clipped to the map
 };
 
-__device__ __forceinline__ void line_init(Line &L, int sx, int sy, int ex, int ey)
+__global__ void __launch_bounds__(kThreads) k_raycast_sweep(
+  unsigned long long *__restrict__ ends, int32_t *__restrict__ hit, int32_t *__restrict__ miss,
+  const SweepEntry *__restrict__ entries, const unsigned *__restrict__ item_prefix, int n_entries,
+  unsigned n_items, int sx, int sy, int nx, unsigned rank, unsigned world,
+  unsigned *__restrict__ counter, unsigned long long *__restrict__ stats)
 {
-  const int dx = ex >= sx ? ex - sx : sx - ex;
-  const int dy = ey >= sy ? ey - sy : sy - ey;
-  L.x = sx;
-  L.y = sy;
-  L.inc1x = L.inc2x = ex >= sx ? 1 : -1;
-  L.inc1y = L.inc2y = ey >= sy ? 1 : -1;
-  if (dx >= dy) {
-    L.inc1x = 0; L.inc2y = 0;
-    L.den = dx; L.num = dx / 2; L.add = dy; L.n = dx + 1;
-  } else {
-    L.inc2x = 0; L.inc1y = 0;
-    L.den = dy; L.num = dy / 2; L.add = dx; L.n = dy + 1;
-  }
-}
-
-__device__ __forceinline__ void line_step(Line &L)
-{
-  L.num += L.add;
-  if (L.num >= L.den) {
-    L.num -= L.den;
-    L.x += L.inc1x;
-    L.y += L.inc1y;
-  }
-  L.x += L.inc2x;
-  L.y += L.inc2y;
-}
-
-__global__ void __launch_bounds__(kThreads) k_raycast_lines(const uint2 *__restrict__ list,
-                                                            const unsigned *__restrict__ list_count,
-                                                            int sx, int sy, int nx,
-                                                            int32_t *__restrict__ miss,
-                                                            unsigned long long *__restrict__ stats)
-{
-  const unsigned count = *list_count;
-  unsigned long long logical = 0, physical = 0, lines = 0;
-  const unsigned stride = gridDim.x * blockDim.x;
-  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
-    const uint2 e = list[i];
-    const int ex = (int)(e.x % (unsigned)nx), ey = (int)(e.x / (unsigned)nx);
-    Line L;
-    line_init(L, sx, sy, ex, ey);
-    for (int k = 0; k + 1 < L.n; ++k) {
-      atomicAdd(miss + (L.x + L.y * nx), (int32_t)e.y);
-      line_step(L);
+  const unsigned lane = threadIdx.x & 31;
+  unsigned long long st_beams = 0, st_logical = 0, st_physical = 0, st_lines = 0;
+  for (;;) {
+    unsigned j = 0;
+    if (lane == 0) j = atomicAdd(counter, 1u);
+    j = __shfl_sync(0xffffffffu, j, 0);
+    const unsigned long long item64 = (unsigned long long)j * world + rank;
+    if (item64 >= n_items) break;
+    const unsigned item = (unsigned)item64;
+    // entry e with item_prefix[e] <= item < item_prefix[e+1]
+    int lo = 0, hi = n_entries;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (item_prefix[mid] <= item) lo = mid;
+      else hi = mid;
     }
-    logical += (unsigned long long)e.y * (unsigned long long)L.n;
-    physical += (unsigned long long)(L.n - 1);
-    lines += 1;
+    const SweepEntry E = entries[lo];
+    const int mi = E.m0 + (int)(item - item_prefix[lo]) * 32 + (int)lane;
+    const bool valid = mi <= E.m1;
+    const int mc = valid ? mi : E.m1;  // out-of-range lanes shadow the last real lane, weight 0
+    const bool xmajor = E.dir < 2;
+    int ex, ey;
+    if (E.dir == 4) { ex = sx; ey = sy; }
+    else if (xmajor) { ex = E.dir == 0 ? sx + E.D : sx - E.D; ey = mc; }
+    else { ey = E.dir == 2 ? sy + E.D : sy - E.D; ex = mc; }
+    const size_t elin = (size_t)ex + (size_t)ey * (size_t)nx;
+    const unsigned long long e = valid ? ends[elin] : 0ull;
+    if (__ballot_sync(0xffffffffu, e != 0ull) == 0u) continue;
+    const unsigned w = (unsigned)(e & 0xffffffffull), hits = (unsigned)(e >> 32);
+    if (e != 0ull) {
+      ends[elin] = 0ull;
+      if (hits) hit[elin] += (int32_t)hits;  // only this lane ever writes hit[elin] in this kernel
+      if (w - hits) atomicAdd(miss + elin, (int32_t)(w - hits));  // other lines pass through it
+      st_beams += w;
+      st_logical += (unsigned long long)w * (unsigned)(E.D + 1);
+      st_lines += 1;
+    }
+    if (E.D == 0) continue;
+    // inclusive warp prefix sum of the weights (loop invariant)
+    unsigned P = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, P, o);
+      if (lane >= (unsigned)o) P += t;
+    }
+    // LineIterator state: den = D, num = D/2, add = minor delta; the major coordinate advances
+    // every step, the minor one when num >= den.
+    const int den = E.D;
+    int num = den / 2;
+    const int dminor = xmajor ? ey - sy : ex - sx;
+    const int add = dminor >= 0 ? dminor : -dminor;
+    const int sminor = dminor >= 0 ? 1 : -1;
+    const int smajor = (E.dir == 0 || E.dir == 2) ? 1 : -1;
+    int major = xmajor ? sx : sy, minor = xmajor ? sy : sx;
+    const int stride_major = xmajor ? 1 : nx, stride_minor = xmajor ? nx : 1;
+    int lin = major * stride_major + minor * stride_minor;
+    const int dlin_major = smajor * stride_major, dlin_minor = sminor * stride_minor;
+#pragma unroll 1
+    for (int k = 0; k < den; ++k) {
+      // runs of equal cells = runs of equal minor coordinate (monotone in the lane index)
+      const int prev = __shfl_up_sync(0xffffffffu, minor, 1);
+      const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || minor != prev);
+      const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
+      const int start = 31 - __clz((int)(heads & (0xffffffffu >> (31 - lane))));
+      const unsigned before = __shfl_sync(0xffffffffu, P, (start + 31) & 31);
+      const unsigned sum = P - (start > 0 ? before : 0u);
+      if (tail && sum) {
+        atomicAdd(miss + lin, (int32_t)sum);
+        ++st_physical;
+      }
+      num += add;
+      if (num >= den) {
+        num -= den;
+        minor += sminor;
+        lin += dlin_minor;
+      }
+      lin += dlin_major;
+    }
   }
-  // warp-reduce the three counters, one atomic each per warp
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    logical += __shfl_xor_sync(0xffffffffu, logical, o);
-    physical += __shfl_xor_sync(0xffffffffu, physical, o);
-    lines += __shfl_xor_sync(0xffffffffu, lines, o);
+    st_beams += __shfl_xor_sync(0xffffffffu, st_beams, o);
+    st_logical += __shfl_xor_sync(0xffffffffu, st_logical, o);
+    st_physical += __shfl_xor_sync(0xffffffffu, st_physical, o);
+    st_lines += __shfl_xor_sync(0xffffffffu, st_lines, o);
   }
-  if ((threadIdx.x & 31) == 0 && lines) {
-    atomicAdd(stats + 0, logical);
-    atomicAdd(stats + 1, physical);
-    atomicAdd(stats + 2, lines);
+  if (lane == 0 && st_lines) {
+    atomicAdd(stats + 0, st_beams);
+    atomicAdd(stats + 1, st_logical);
+    atomicAdd(stats + 2, st_physical);
+    atomicAdd(stats + 3, st_lines);
   }
 }
 
