@@ -167,6 +167,88 @@ def run_reference_arm(args, wl):
     }))
 
 
+def measured_traffic():
+    """DRAM bytes per point of the fused kernel from the committed ncu capture (profiles/)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+def time_loop(torch, fn, iters, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def other_configs(torch, gv, synth, ctx, dev):
+    """The remaining BASELINE.json configs, resident inputs, CUDA-event timed (N = 1 only).
+    Each entry: milliseconds per pass and points/s; parity for every one of them is in tests/."""
+    out = {}
+    # C1 / C2: one scan -> fuse + bin + raycast + finalise (latency-bound: a few launches)
+    for wl in (synth.C1, synth.C2):
+        xyz = synth.make_scans(wl, frames=1, device=dev)
+        boxes = synth.make_boxes(wl)
+        d_boxes = torch.from_numpy(boxes.view(np.uint8).copy()).to(dev)
+        lab = torch.empty(wl.points, dtype=torch.int16, device=dev)
+        fo = np.array([0, wl.points], np.uint64)
+        bo = np.array([0, len(boxes)], np.int32)
+        ctx.grid_init_cells(wl.grid_nx, wl.grid_ny, wl.resolution)
+        ctx.set_base_transform(synth.T_base_lidar())
+        prm = gv.accum_params(r_max=wl.r_max)
+
+        def one():
+            ctx.process_batch(xyz[0], xyz[1], xyz[2], fo, d_boxes, bo, prm, lab)
+            ctx.grid_finalize(1)
+        ms = time_loop(torch, one, 50)
+        out[f"C{wl.config_id}"] = {"workload": wl.name, "ms": ms, "points_per_s": wl.points / (ms * 1e-3)}
+    # C4: 6-camera rig, 300 boxes, 1M-point cloud (fusion only, one label plane per camera)
+    wl = synth.C4
+    xyz = synth.make_scans(wl, frames=1, device=dev)
+    per_cam = [synth.make_boxes(wl, camera=c) for c in range(6)]
+    boxes = np.concatenate(per_cam)
+    off = np.cumsum([0] + [len(b) for b in per_cam]).astype(np.int32)
+    d_boxes = torch.from_numpy(boxes.view(np.uint8).copy()).to(dev)
+    lab6 = torch.empty((6, wl.points), dtype=torch.int16, device=dev)
+    ctx.set_cameras(np.tile(wl.K().reshape(1, 9), (6, 1)), [[wl.image_w, wl.image_h]] * 6,
+                    synth.camera_extrinsics(6))
+    ms = time_loop(torch, lambda: ctx.fuse_dev(xyz[0], xyz[1], xyz[2], d_boxes, len(boxes), off, labels=lab6), 50)
+    out["C4"] = {"workload": wl.name, "ms": ms, "points_per_s": wl.points / (ms * 1e-3),
+                 "camera_projections_per_s": 6 * wl.points / (ms * 1e-3)}
+    ctx.set_cameras(wl.K().reshape(1, 9), [[wl.image_w, wl.image_h]], synth.camera_extrinsics(1))
+    # C5: 8192x8192 grid @0.05 m, 16.7M points per batch, 120 m rays
+    wl = synth.C5
+    xyz = synth.make_scans(wl, device=dev)
+    boxes = np.concatenate([synth.make_boxes(wl, frame=f) for f in range(wl.frames)])
+    d_boxes = torch.from_numpy(boxes.view(np.uint8).copy()).to(dev)
+    lab = torch.empty(wl.points, dtype=torch.int16, device=dev)
+    fo = np.arange(wl.frames + 1, dtype=np.uint64) * np.uint64(wl.points_per_frame)
+    bo = (np.arange(wl.frames + 1) * wl.boxes_per_camera).astype(np.int32)
+    ctx.grid_init_cells(wl.grid_nx, wl.grid_ny, wl.resolution)
+    ctx.set_base_transform(synth.T_base_lidar())
+    prm = gv.accum_params(r_max=wl.r_max)
+    st0 = ctx.stats()
+
+    def one5():
+        ctx.process_batch(xyz[0], xyz[1], xyz[2], fo, d_boxes, bo, prm, lab)
+        ctx.grid_finalize(wl.frames)
+    ms = time_loop(torch, one5, 10)
+    st1 = ctx.stats()
+    passes = 13
+    out["C5"] = {"workload": wl.name, "ms": ms, "points_per_s": wl.points / (ms * 1e-3),
+                 "cells_logical_per_s": (st1["cells_logical"] - st0["cells_logical"]) / passes / (ms * 1e-3),
+                 "grid_cells": wl.cells}
+    return out
+
+
 def workload_config(wl, frames, gpus, **extra):
     c = {"workload": f"C3 batched replay: {frames} synthetic 64-beam scans x {wl.points_per_frame} pts, "
                      f"{wl.boxes_per_camera} boxes/scan, 416x416 camera, {wl.grid_nx}x{wl.grid_ny} grid "
@@ -189,6 +271,7 @@ def main():
     ap.add_argument("--frames", type=int, default=0, help="total frames in the batch (default 4096)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the C1/C2/C4/C5 side measurements")
     args = ap.parse_args()
 
     from grid_vision_b200 import synth
@@ -232,8 +315,12 @@ def main():
     ctx.set_cameras(wl.K().reshape(1, 9), [[wl.image_w, wl.image_h]], synth.camera_extrinsics(1))
     ctx.grid_init_cells(wl.grid_nx, wl.grid_ny, wl.resolution)
     ctx.set_base_transform(synth.T_base_lidar())
+    merge = "single GPU"
     if world > 1:
         sharding.init_context_comm(ctx, dev)
+        merge = "NCCL all-reduce + reduce-scatter + all-gather"
+        if os.environ.get("GV_MERGE", "p2p") == "p2p" and sharding.enable_p2p(ctx, dev):
+            merge = "fused over NVLink peer memory (sweep sums peers' planes, finalise writes peers' grids)"
     multi = world > 1
 
     def step_resident(ev=None):
@@ -339,7 +426,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None,
             "dtype": "f32 transform / f64 projection+indices / i32 counts", "data": "synthetic",
-            "config": workload_config(wl, F, world),
+            "config": workload_config(wl, F, world, merge=merge),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "gv::k_points<true,true> (fused transform+project+label+bin)",
                          "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
@@ -350,6 +437,12 @@ def main():
                             "physical": (st1["cells_physical"] - st0["cells_physical"]) / args.steps / (ms_step * 1e-3),
                             "distinct_ends_per_step": dst / args.steps},
         }
+        tr = measured_traffic()
+        if tr:
+            out["roofline"]["traffic"] = tr["dram_bytes_per_point"] * n_local
+            out["roofline"]["traffic_source"] = tr["source"]
+        if world == 1 and not args.no_extra:
+            out["other_configs"] = other_configs(torch, gv, synth, ctx, dev)
         if not args.no_cpu and world == 1:
             cores = os.cpu_count() or 1
             frames = max(2, min(2 * cores, 64))

@@ -319,6 +319,16 @@ class Context:
             raise GridVisionError(rc, "gv_nccl_unique_id")
         return buf.raw
 
+    def ipc_export(self) -> bytes:
+        buf = C.create_string_buffer(320)
+        self._check(self._lib.gv_ipc_export(self._h, buf), "gv_ipc_export")
+        return buf.raw
+
+    def ipc_import(self, blobs: bytes, world: int, rank: int):
+        assert len(blobs) == 320 * world
+        self._check(self._lib.gv_ipc_import(self._h, C.c_char_p(blobs), C.c_int(world), C.c_int(rank)),
+                    "gv_ipc_import")
+
     def nccl_init(self, unique_id: bytes, rank: int, world: int):
         assert len(unique_id) == 128
         self._check(self._lib.gv_nccl_init(self._h, C.c_char_p(unique_id), C.c_int(rank),

@@ -77,6 +77,12 @@ struct gv_ctx {
   ncclComm_t comm = nullptr;
 #endif
   int rank = 0, world = 1;
+  // peer-memory (cudaIpc) views of every rank's planes; [rank] is the local pointer
+  bool p2p = false;
+  Peers<unsigned long long> peer_ends{};
+  Peers<int32_t> peer_hit{}, peer_miss{};
+  Peers<float> peer_lo{}, peer_occ{};
+  int *d_barrier = nullptr;
 
   int fail(int code, const char *fmt, ...)
   {
@@ -387,22 +393,28 @@ int accumulate_dev_impl(gv_ctx *ctx, const float *d_x, const float *d_y, const f
   return launch_points(ctx, false, true, a, blocks_for(n, a.tile_pts), 32);
 }
 
-int raycast_flush_impl(gv_ctx *ctx, unsigned rank, unsigned world)
+int raycast_flush_impl(gv_ctx *ctx, unsigned rank, unsigned world, bool p2p_sweep = false)
 {
   if (!ctx->ends_dirty) return GV_OK;
   ctx->ends_dirty = false;
   if (!ctx->bin.origin_ok || ctx->n_sweep_items == 0) return GV_OK;  // nothing was binned
   GV_CUDA(cudaMemsetAsync(ctx->d_list_count, 0, sizeof(unsigned), ctx->stream));
   const unsigned nb = (unsigned)ctx->num_sms * 8u;
-  k_raycast_sweep<<<nb, kThreads, 0, ctx->stream>>>(ctx->d_ends, ctx->d_hit, ctx->d_miss, ctx->d_sweep,
-                                                    ctx->d_sweep_prefix, ctx->n_sweep,
-                                                    ctx->n_sweep_items, ctx->bin.sx, ctx->bin.sy,
-                                                    ctx->g.nx, rank, world, ctx->d_list_count,
-                                                    ctx->d_stats);
+  if (p2p_sweep)
+    k_raycast_sweep<true><<<nb, kThreads, 0, ctx->stream>>>(
+      ctx->d_ends, ctx->d_hit, ctx->d_miss, ctx->d_sweep, ctx->d_sweep_prefix, ctx->n_sweep,
+      ctx->n_sweep_items, ctx->bin.sx, ctx->bin.sy, ctx->g.nx, rank, world, ctx->d_list_count,
+      ctx->d_stats, ctx->peer_ends);
+  else
+    k_raycast_sweep<false><<<nb, kThreads, 0, ctx->stream>>>(
+      ctx->d_ends, ctx->d_hit, ctx->d_miss, ctx->d_sweep, ctx->d_sweep_prefix, ctx->n_sweep,
+      ctx->n_sweep_items, ctx->bin.sx, ctx->bin.sy, ctx->g.nx, rank, world, ctx->d_list_count,
+      ctx->d_stats, ctx->peer_ends);
   GV_LAUNCH_CHECK();
-  // multi-GPU: this rank settled and cleared only the end cells of its own work items; the
-  // entries owned by the other ranks were handled there, drop them
-  if (world > 1)
+  // NCCL multi-GPU path: this rank settled and cleared only the end cells of its own work
+  // items; the entries owned by the other ranks were handled there, drop them.  (The P2P sweep
+  // clears every rank's entries itself.)
+  if (world > 1 && !p2p_sweep)
     GV_CUDA(cudaMemsetAsync(ctx->d_ends, 0, ctx->ncells * sizeof(unsigned long long), ctx->stream));
   ctx->counts_dirty = true;
   return GV_OK;
@@ -491,10 +503,15 @@ int footprint_rects(gv_ctx *ctx, const double *in, const int32_t *labels, int n,
 }
 
 int finalize_slab(gv_ctx *ctx, int32_t k_decay, const int4 *d_rects, int nfoot, size_t cell0,
-                  size_t ncell, bool counts)
+                  size_t ncell, bool counts, bool p2p = false)
 {
   if (ncell == 0) return GV_OK;
   FinalizeArgs fa;
+  fa.world = ctx->world;
+  fa.peer_lo = ctx->peer_lo;
+  fa.peer_occ = ctx->peer_occ;
+  fa.peer_hit = ctx->peer_hit;
+  fa.peer_miss = ctx->peer_miss;
   fa.log_odds = ctx->d_lo;
   fa.occupancy = ctx->d_occ;
   fa.hit = ctx->d_hit;
@@ -506,8 +523,9 @@ int finalize_slab(gv_ctx *ctx, int32_t k_decay, const int4 *d_rects, int nfoot, 
   fa.rects = d_rects;
   fa.nfoot = d_rects ? nfoot : 0;
   const unsigned nb = blocks_for(ncell, kThreads * 4);
-  if (counts) k_finalize<true><<<nb, kThreads, 0, ctx->stream>>>(fa);
-  else k_finalize<false><<<nb, kThreads, 0, ctx->stream>>>(fa);
+  if (p2p) k_finalize<true, true><<<nb, kThreads, 0, ctx->stream>>>(fa);
+  else if (counts) k_finalize<true, false><<<nb, kThreads, 0, ctx->stream>>>(fa);
+  else k_finalize<false, false><<<nb, kThreads, 0, ctx->stream>>>(fa);
   GV_LAUNCH_CHECK();
   return GV_OK;
 }
@@ -526,8 +544,29 @@ int finalize_impl(gv_ctx *ctx, int32_t k_decay, const double *in, const int32_t 
   return GV_OK;
 }
 
+void close_peers(gv_ctx *ctx)
+{
+  if (!ctx->p2p) return;
+  for (int r = 0; r < ctx->world && r < kMaxPeers; ++r) {
+    if (r == ctx->rank) continue;
+    if (ctx->peer_ends.p[r]) cudaIpcCloseMemHandle(ctx->peer_ends.p[r]);
+    if (ctx->peer_hit.p[r]) cudaIpcCloseMemHandle(ctx->peer_hit.p[r]);
+    if (ctx->peer_miss.p[r]) cudaIpcCloseMemHandle(ctx->peer_miss.p[r]);
+    if (ctx->peer_lo.p[r]) cudaIpcCloseMemHandle(ctx->peer_lo.p[r]);
+    if (ctx->peer_occ.p[r]) cudaIpcCloseMemHandle(ctx->peer_occ.p[r]);
+  }
+  ctx->peer_ends = {};
+  ctx->peer_hit = {};
+  ctx->peer_miss = {};
+  ctx->peer_lo = {};
+  ctx->peer_occ = {};
+  ctx->p2p = false;
+  cudaGetLastError();
+}
+
 void free_grid(gv_ctx *ctx)
 {
+  close_peers(ctx);
   cudaFree(ctx->d_lo);
   cudaFree(ctx->d_occ);
   cudaFree(ctx->d_hit);
@@ -694,6 +733,7 @@ void gv_destroy(gv_ctx *ctx)
   for (auto &s : ctx->s) cudaFree(s.p);
   cudaFree(ctx->d_stats);
   cudaFree(ctx->d_list_count);
+  cudaFree(ctx->d_barrier);
   for (auto e : ctx->events) cudaEventDestroy(e);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
@@ -1467,6 +1507,30 @@ int gv_grid_finalize_multi(gv_ctx *ctx, int32_t k_decay, const double *corners, 
   size_t slab = (ctx->ncells + world - 1) / world;
   slab = (slab + 3) & ~(size_t)3;
   GV_REQUIRE(slab * world <= ctx->ncells + kPlanePad, GV_ERR_INVALID, "grid too small for %u ranks", world);
+  if (ctx->p2p) {
+    // ---- fused over peer memory (NVLink P2P): NCCL only for one-word stream barriers
+    if (!ctx->d_barrier) {
+      GV_CUDA(cudaMalloc(&ctx->d_barrier, sizeof(int)));
+      GV_CUDA(cudaMemsetAsync(ctx->d_barrier, 0, sizeof(int), ctx->stream));
+    }
+    auto barrier = [&]() -> int {
+      GV_NCCL(ncclAllReduce(ctx->d_barrier, ctx->d_barrier, 1, ncclInt32, ncclSum, ctx->comm, ctx->stream));
+      return GV_OK;
+    };
+    GV_TRY(barrier());  // every rank has finished binning into its ends plane
+    ctx->ends_dirty = true;
+    GV_TRY(raycast_flush_impl(ctx, rank, world, true));  // sums + clears all ranks' ends entries
+    GV_TRY(barrier());  // every rank's partial hit/miss planes are complete
+    int4 *d_rects = nullptr;
+    GV_TRY(footprint_rects(ctx, corners, nullptr, nfoot, 0, &d_rects));
+    const size_t c0 = (size_t)rank * slab;
+    const size_t c1 = c0 + slab < ctx->ncells ? c0 + slab : ctx->ncells;
+    if (c1 > c0) GV_TRY(finalize_slab(ctx, k_decay, d_rects, nfoot, c0, c1 - c0, true, true));
+    GV_TRY(barrier());  // every slab has been written into every rank's grid, counts cleared
+    ctx->counts_dirty = false;
+    ctx->beams_bound = 0;
+    return GV_OK;
+  }
   // 1. every rank learns every rank's binned beams: exact u64 sum of the (total,hit) plane
   GV_NCCL(ncclAllReduce(ctx->d_ends, ctx->d_ends, ctx->ncells, ncclUint64, ncclSum, ctx->comm,
                         ctx->stream));
@@ -1501,6 +1565,66 @@ int gv_grid_finalize_multi(gv_ctx *ctx, int32_t k_decay, const double *corners, 
   if (ctx->world == 1) return finalize_impl(ctx, k_decay, corners, nullptr, nfoot, 0);
   return ctx->fail(GV_ERR_NCCL, "library built without NCCL");
 #endif
+}
+
+int gv_ipc_export(gv_ctx *ctx, void *blob_out)
+{
+  if (!ctx) return GV_ERR_INVALID;
+  GV_CUDA(cudaSetDevice(ctx->device));
+  GV_REQUIRE(ctx->has_grid, GV_ERR_STATE, "grid not initialised");
+  GV_REQUIRE(blob_out != nullptr, GV_ERR_INVALID, "blob_out is NULL");
+  static_assert(5 * sizeof(cudaIpcMemHandle_t) == GV_IPC_BLOB_BYTES, "ipc blob size");
+  cudaIpcMemHandle_t h[5];
+  GV_CUDA(cudaIpcGetMemHandle(&h[0], ctx->d_ends));
+  GV_CUDA(cudaIpcGetMemHandle(&h[1], ctx->d_hit));
+  GV_CUDA(cudaIpcGetMemHandle(&h[2], ctx->d_miss));
+  GV_CUDA(cudaIpcGetMemHandle(&h[3], ctx->d_lo));
+  GV_CUDA(cudaIpcGetMemHandle(&h[4], ctx->d_occ));
+  memcpy(blob_out, h, sizeof(h));
+  return GV_OK;
+}
+
+int gv_ipc_import(gv_ctx *ctx, const void *blobs, int world, int rank)
+{
+  if (!ctx) return GV_ERR_INVALID;
+  GV_CUDA(cudaSetDevice(ctx->device));
+  GV_REQUIRE(ctx->has_grid, GV_ERR_STATE, "grid not initialised");
+  GV_REQUIRE(blobs && world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, GV_ERR_INVALID,
+             "bad rank/world %d/%d (at most %d peers)", rank, world, kMaxPeers);
+  GV_REQUIRE(world == ctx->world && rank == ctx->rank, GV_ERR_STATE,
+             "gv_nccl_init must come first (barriers) and agree on rank/world");
+  GV_CUDA(cudaStreamSynchronize(ctx->stream));
+  close_peers(ctx);
+  ctx->p2p = true;  // so that close_peers cleans up a partial import
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) {
+      ctx->peer_ends.p[r] = ctx->d_ends;
+      ctx->peer_hit.p[r] = ctx->d_hit;
+      ctx->peer_miss.p[r] = ctx->d_miss;
+      ctx->peer_lo.p[r] = ctx->d_lo;
+      ctx->peer_occ.p[r] = ctx->d_occ;
+      continue;
+    }
+    cudaIpcMemHandle_t h[5];
+    memcpy(h, static_cast<const char *>(blobs) + (size_t)r * GV_IPC_BLOB_BYTES, sizeof(h));
+    void *q[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    for (int k = 0; k < 5; ++k) {
+      const cudaError_t e = cudaIpcOpenMemHandle(&q[k], h[k], cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        for (int m = 0; m < k; ++m) cudaIpcCloseMemHandle(q[m]);
+        close_peers(ctx);
+        return ctx->fail(GV_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d, plane %d): %s", r, k,
+                         cudaGetErrorString(e));
+      }
+    }
+    ctx->peer_ends.p[r] = static_cast<unsigned long long *>(q[0]);
+    ctx->peer_hit.p[r] = static_cast<int32_t *>(q[1]);
+    ctx->peer_miss.p[r] = static_cast<int32_t *>(q[2]);
+    ctx->peer_lo.p[r] = static_cast<float *>(q[3]);
+    ctx->peer_occ.p[r] = static_cast<float *>(q[4]);
+  }
+  return GV_OK;
 }
 
 }  // extern "C"

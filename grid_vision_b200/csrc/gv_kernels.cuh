@@ -827,17 +827,29 @@ __global__ void __launch_bounds__(kThreads) k_label_scatter(const int16_t *__res
 // on every rank).
 // grid_map LineIterator restatement: oracle gvo_line_init / gvo_line_step.
 // ----------------------------------------------------------------------------------
+// Peer-memory views of one plane on every rank (cudaIpc-mapped, NVLink P2P); p[rank] is local.
+constexpr int kMaxPeers = 16;
+template <typename T>
+struct Peers {
+  T *p[kMaxPeers];
+};
+
 struct SweepEntry {
   int dir;  // 0: x = sx + D, 1: x = sx - D (x-major); 2: y = sy + D, 3: y = sy - D (y-major); 4: origin
   int D;
   int m0, m1;  // inclusive range of the minor coordinate (absolute index), clipped to the map
 };
 
+// P2P = true (gv_grid_finalize_multi over peer memory): the owner of an item sums the end-cell
+// entries of ALL ranks' planes with NVLink loads and clears them with NVLink stores — the
+// all-reduce of the ends plane is fused into the sweep; hit/miss stay rank-local partial planes.
+template <bool P2P>
 __global__ void __launch_bounds__(kThreads) k_raycast_sweep(
   unsigned long long *__restrict__ ends, int32_t *__restrict__ hit, int32_t *__restrict__ miss,
   const SweepEntry *__restrict__ entries, const unsigned *__restrict__ item_prefix, int n_entries,
   unsigned n_items, int sx, int sy, int nx, unsigned rank, unsigned world,
-  unsigned *__restrict__ counter, unsigned long long *__restrict__ stats)
+  unsigned *__restrict__ counter, unsigned long long *__restrict__ stats,
+  const __grid_constant__ Peers<unsigned long long> peer_ends)
 {
   const unsigned lane = threadIdx.x & 31;
   unsigned long long st_beams = 0, st_logical = 0, st_physical = 0, st_lines = 0;
@@ -865,11 +877,25 @@ __global__ void __launch_bounds__(kThreads) k_raycast_sweep(
     else if (xmajor) { ex = E.dir == 0 ? sx + E.D : sx - E.D; ey = mc; }
     else { ey = E.dir == 2 ? sy + E.D : sy - E.D; ex = mc; }
     const size_t elin = (size_t)ex + (size_t)ey * (size_t)nx;
-    const unsigned long long e = valid ? ends[elin] : 0ull;
+    unsigned long long e = 0ull;
+    if (P2P) {
+      if (valid) {
+        unsigned long long part[kMaxPeers];
+#pragma unroll
+        for (int r = 0; r < kMaxPeers; ++r) part[r] = r < (int)world ? peer_ends.p[r][elin] : 0ull;
+#pragma unroll
+        for (int r = 0; r < kMaxPeers; ++r) {
+          e += part[r];
+          if (part[r] != 0ull) peer_ends.p[r][elin] = 0ull;
+        }
+      }
+    } else {
+      e = valid ? ends[elin] : 0ull;
+    }
     if (__ballot_sync(0xffffffffu, e != 0ull) == 0u) continue;
     const unsigned w = (unsigned)(e & 0xffffffffull), hits = (unsigned)(e >> 32);
     if (e != 0ull) {
-      ends[elin] = 0ull;
+      if (!P2P) ends[elin] = 0ull;
       if (hits) hit[elin] += (int32_t)hits;  // only this lane ever writes hit[elin] in this kernel
       if (w - hits) atomicAdd(miss + elin, (int32_t)(w - hits));  // other lines pass through it
       st_beams += w;
@@ -1020,6 +1046,11 @@ __global__ void k_get_index(const double *__restrict__ xy, int n, const __grid_c
 struct FinalizeArgs {
   float *log_odds, *occupancy;
   int32_t *hit, *miss;
+  // P2P: every rank's planes; the slab owner sums all ranks' counts (fused reduce-scatter),
+  // writes log-odds/occupancy into every rank's grid (fused all-gather) and clears the counts
+  int world;
+  Peers<float> peer_lo, peer_occ;
+  Peers<int32_t> peer_hit, peer_miss;
   unsigned long long cell0, ncell;  // slab [cell0, cell0+ncell), cell0 % 4 == 0
   int nx;
   float decay;  // (float)k_decay * -0.2f, computed on the host in float
@@ -1027,7 +1058,7 @@ struct FinalizeArgs {
   int nfoot;
 };
 
-template <bool COUNTS>
+template <bool COUNTS, bool P2P>
 __global__ void __launch_bounds__(kThreads) k_finalize(const __grid_constant__ FinalizeArgs a)
 {
   __shared__ int4 s_rect[kMaxFootCand];
@@ -1060,21 +1091,34 @@ __global__ void __launch_bounds__(kThreads) k_finalize(const __grid_constant__ F
   if (full) {
     const float4 v = *reinterpret_cast<const float4 *>(a.log_odds + i0);
     l[0] = v.x; l[1] = v.y; l[2] = v.z; l[3] = v.w;
-    if (COUNTS) {
+    if (COUNTS && !P2P) {
       const int4 hv = *reinterpret_cast<const int4 *>(a.hit + i0);
       const int4 mv = *reinterpret_cast<const int4 *>(a.miss + i0);
       h[0] = hv.x; h[1] = hv.y; h[2] = hv.z; h[3] = hv.w;
       m[0] = mv.x; m[1] = mv.y; m[2] = mv.z; m[3] = mv.w;
+    }
+    if (COUNTS && P2P) {
+      for (int r = 0; r < a.world; ++r) {
+        const int4 hv = *reinterpret_cast<const int4 *>(a.peer_hit.p[r] + i0);
+        const int4 mv = *reinterpret_cast<const int4 *>(a.peer_miss.p[r] + i0);
+        h[0] += hv.x; h[1] += hv.y; h[2] += hv.z; h[3] += hv.w;
+        m[0] += mv.x; m[1] += mv.y; m[2] += mv.z; m[3] += mv.w;
+      }
     }
   } else {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const bool ok = i0 + j < endc;
       l[j] = ok ? a.log_odds[i0 + j] : 0.0f;
-      if (COUNTS && ok) {
+      if (COUNTS && ok && !P2P) {
         h[j] = a.hit[i0 + j];
         m[j] = a.miss[i0 + j];
       }
+      if (COUNTS && ok && P2P)
+        for (int r = 0; r < a.world; ++r) {
+          h[j] += a.peer_hit.p[r][i0 + j];
+          m[j] += a.peer_miss.p[r][i0 + j];
+        }
     }
   }
   int ix = (int)(i0 % (unsigned)a.nx), iy = (int)(i0 / (unsigned)a.nx);
@@ -1110,7 +1154,28 @@ __global__ void __launch_bounds__(kThreads) k_finalize(const __grid_constant__ F
       ++iy;
     }
   }
-  if (full) {
+  if (full && P2P) {
+    for (int r = 0; r < a.world; ++r) {
+      *reinterpret_cast<float4 *>(a.peer_lo.p[r] + i0) = make_float4(l[0], l[1], l[2], l[3]);
+      *reinterpret_cast<float4 *>(a.peer_occ.p[r] + i0) = make_float4(o[0], o[1], o[2], o[3]);
+      if (COUNTS) {
+        *reinterpret_cast<int4 *>(a.peer_hit.p[r] + i0) = make_int4(0, 0, 0, 0);
+        *reinterpret_cast<int4 *>(a.peer_miss.p[r] + i0) = make_int4(0, 0, 0, 0);
+      }
+    }
+  } else if (!full && P2P) {
+    for (int r = 0; r < a.world; ++r)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (i0 + j < endc) {
+          a.peer_lo.p[r][i0 + j] = l[j];
+          a.peer_occ.p[r][i0 + j] = o[j];
+          if (COUNTS) {
+            a.peer_hit.p[r][i0 + j] = 0;
+            a.peer_miss.p[r][i0 + j] = 0;
+          }
+        }
+  } else if (full) {
     *reinterpret_cast<float4 *>(a.log_odds + i0) = make_float4(l[0], l[1], l[2], l[3]);
     *reinterpret_cast<float4 *>(a.occupancy + i0) = make_float4(o[0], o[1], o[2], o[3]);
     if (COUNTS) {

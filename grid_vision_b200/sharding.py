@@ -44,3 +44,31 @@ def init_context_comm(ctx, device="cuda"):
     uid = ctx.nccl_unique_id() if rank == 0 else None
     uid = broadcast_bytes(uid, 128, 0, device)
     ctx.nccl_init(uid, rank, world)
+
+
+def enable_p2p(ctx, device="cuda") -> bool:
+    """Map every rank's grid planes into every rank (cudaIpc, NVLink P2P) so that
+    gv_grid_finalize_multi runs fused over peer memory.  Call after grid_init on every rank.
+    Returns False (and leaves the NCCL path active) if any rank cannot map its peers."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    if world == 1:
+        return False
+    mine = torch.frombuffer(bytearray(ctx.ipc_export()), dtype=torch.uint8).to(device)
+    allb = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allb, mine)
+    blobs = b"".join(bytes(t.cpu().numpy().tobytes()) for t in allb)
+    ok = 1
+    try:
+        ctx.ipc_import(blobs, world, rank)
+    except Exception as e:  # noqa: BLE001
+        if rank == 0:
+            print(f"[grid_vision_b200] peer-memory mapping unavailable, staying on NCCL collectives: {e}")
+        ok = 0
+    t = torch.tensor([ok], dtype=torch.int32, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if int(t.item()) == 0 and ok:
+        # someone failed: every rank must use the same path
+        raise RuntimeError("inconsistent peer-memory mapping across ranks")
+    return bool(int(t.item()))

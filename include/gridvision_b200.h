@@ -240,6 +240,16 @@ GV_API int gv_nccl_world(gv_ctx *ctx, int *rank_out, int *world_out);
  * every rank finalises its slab of the grid and the slabs are all-gathered, so each rank
  * ends with the identical full grid.  Bit-identical to a single-context run. */
 GV_API int gv_grid_finalize_multi(gv_ctx *ctx, int32_t k_decay, const double *corners, int nfoot);
+/* Optional: map every rank's grid planes into every other rank (cudaIpc over NVLink P2P) so
+ * that gv_grid_finalize_multi runs FUSED over peer memory: the raycast sweep sums and clears the
+ * binned-beam planes of all ranks itself (no all-reduce), and the finalise kernel sums all
+ * ranks' count planes for its slab and writes the finished slab into every rank's grid (no
+ * reduce-scatter / all-gather); NCCL is then used only for three one-word barriers.
+ * Call gv_ipc_export on every rank after gv_grid_init*, exchange the GV_IPC_BLOB_BYTES blobs
+ * (rank order), call gv_ipc_import on every rank.  Re-do after re-initialising the grid. */
+#define GV_IPC_BLOB_BYTES 320
+GV_API int gv_ipc_export(gv_ctx *ctx, void *blob_out);
+GV_API int gv_ipc_import(gv_ctx *ctx, const void *blobs, int world, int rank);
 
 #ifdef __cplusplus
 }

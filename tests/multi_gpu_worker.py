@@ -31,6 +31,9 @@ def main():
     ctx.grid_init_cells(wl.grid_nx, wl.grid_ny, wl.resolution)
     ctx.set_base_transform(Tb)
     sharding.init_context_comm(ctx, torch.device("cuda", local))
+    mode = os.environ.get("GV_MULTI_MODE", "nccl")
+    if mode == "p2p":
+        assert sharding.enable_p2p(ctx, torch.device("cuda", local)), "peer mapping failed"
     prm = dict(occ_mode=gv.OCC_LABELLED, r_max=wl.r_max)
     corners = orc.pose_corners(synth.make_footprints(wl, n=6))
     g = orc.Grid.from_cells(wl.grid_nx, wl.grid_ny, wl.resolution)
@@ -55,7 +58,7 @@ def main():
     ctx.close()
     dist.barrier()
     if rank == 0:
-        print(f"MULTI_GPU_OK world={world}")
+        print(f"MULTI_GPU_OK world={world} mode={mode}")
     dist.destroy_process_group()
 
 
