@@ -72,6 +72,13 @@ struct gv_ctx {
   unsigned long long beams_bound = 0;  // host-side upper bound of beams since last finalize
 
   Scratch s[S_COUNT];
+  // batch tables of the previous gv_process_batch call (frame layout rarely changes between
+  // calls of a replay: identical offsets skip the upload, the tile-table kernel and any sync)
+  std::vector<unsigned long long> c_foff;
+  std::vector<int> c_boff;
+  std::vector<unsigned> c_tile_prefix;
+  int c_tile_pts = 0, c_max_boxes = 0;
+  bool c_valid = false;
 
 #ifdef GV_WITH_NCCL
   ncclComm_t comm = nullptr;
@@ -1260,23 +1267,40 @@ static int process_batch_impl(gv_ctx *ctx, const float *px, const float *py, con
   GV_TRY(set_bin_params(ctx, prm, &a.bin));
   GV_TRY(note_beams(ctx, n));
 
+  // points: device-resident, or staged per chunk from host memory
+  const uint64_t base = points_on_device ? 0 : p0;  // host path rebases the staged copy to 0
   // tile table: one entry per CTA tile, tiles never straddle frames
   const int tile_pts = tile_points_for(n, ctx->num_sms);
-  std::vector<unsigned> tile_prefix((size_t)nframes + 1);
-  int max_boxes = 1;
-  unsigned long long ntiles64 = 0;
-  for (int f = 0; f < nframes; ++f) {
-    GV_REQUIRE(frame_offsets[f + 1] >= frame_offsets[f], GV_ERR_INVALID,
-               "frame_offsets not monotone at %d", f);
-    const int nb = box_frame_offsets[f + 1] - box_frame_offsets[f];
-    GV_REQUIRE(nb >= 0 && nb <= 32767, GV_ERR_INVALID, "frame %d has %d boxes", f, nb);
-    if (nb > max_boxes) max_boxes = nb;
-    tile_prefix[f] = (unsigned)ntiles64;
-    ntiles64 += (frame_offsets[f + 1] - frame_offsets[f] + tile_pts - 1) / tile_pts;
-    GV_REQUIRE(ntiles64 < 2147483647ull, GV_ERR_INVALID, "batch too large");
+  bool same = ctx->c_valid && ctx->c_tile_pts == tile_pts && (int)ctx->c_boff.size() == nframes + 1 &&
+              (int)ctx->c_foff.size() == nframes + 1 &&
+              memcmp(ctx->c_boff.data(), box_frame_offsets, ((size_t)nframes + 1) * sizeof(int)) == 0;
+  if (same)
+    for (int f = 0; f <= nframes && same; ++f) same = ctx->c_foff[f] == frame_offsets[f] - base;
+  if (!same) {
+    ctx->c_valid = false;
+    ctx->c_foff.resize((size_t)nframes + 1);
+    ctx->c_boff.assign(box_frame_offsets, box_frame_offsets + nframes + 1);
+    ctx->c_tile_prefix.resize((size_t)nframes + 1);
+    ctx->c_tile_pts = tile_pts;
+    ctx->c_max_boxes = 1;
+    unsigned long long ntiles64 = 0;
+    for (int f = 0; f < nframes; ++f) {
+      GV_REQUIRE(frame_offsets[f + 1] >= frame_offsets[f], GV_ERR_INVALID,
+                 "frame_offsets not monotone at %d", f);
+      const int nb = box_frame_offsets[f + 1] - box_frame_offsets[f];
+      GV_REQUIRE(nb >= 0 && nb <= 32767, GV_ERR_INVALID, "frame %d has %d boxes", f, nb);
+      if (nb > ctx->c_max_boxes) ctx->c_max_boxes = nb;
+      ctx->c_tile_prefix[f] = (unsigned)ntiles64;
+      ntiles64 += (frame_offsets[f + 1] - frame_offsets[f] + tile_pts - 1) / tile_pts;
+      GV_REQUIRE(ntiles64 < 2147483647ull, GV_ERR_INVALID, "batch too large");
+    }
+    ctx->c_tile_prefix[nframes] = (unsigned)ntiles64;
+    for (int f = 0; f <= nframes; ++f) ctx->c_foff[f] = frame_offsets[f] - base;
   }
-  tile_prefix[nframes] = (unsigned)ntiles64;
-  const unsigned ntiles = (unsigned)ntiles64;
+  const std::vector<unsigned long long> &foff = ctx->c_foff;
+  const std::vector<unsigned> &tile_prefix = ctx->c_tile_prefix;
+  const int max_boxes = ctx->c_max_boxes;
+  const unsigned ntiles = tile_prefix[nframes];
 
   unsigned long long *d_foff, *d_tstart, *d_tend;
   int *d_boff;
@@ -1289,10 +1313,8 @@ static int process_batch_impl(gv_ctx *ctx, const float *px, const float *py, con
   GV_TRY(reserve_t(ctx, S_TILE_END, (size_t)ntiles, &d_tend));
   GV_TRY(reserve_t(ctx, S_TILE_BOX, (size_t)ntiles, &d_tbox));
 
-  // points: device-resident, or staged per chunk from host memory
   const float *d_x = px, *d_y = py, *d_z = pz;
   int16_t *d_lab = labels_out;
-  uint64_t base = 0;  // offset subtracted from frame offsets (host path rebases to 0)
   if (!points_on_device) {
     float *tx, *ty, *tz;
     GV_TRY(reserve_t(ctx, S_X, n, &tx));
@@ -1301,21 +1323,22 @@ static int process_batch_impl(gv_ctx *ctx, const float *px, const float *py, con
     d_x = tx;
     d_y = ty;
     d_z = tz;
-    base = p0;
     if (labels_out) GV_TRY(reserve_t(ctx, S_LAB, n, &d_lab));
   }
-  std::vector<unsigned long long> foff((size_t)nframes + 1);
-  for (int f = 0; f <= nframes; ++f) foff[f] = frame_offsets[f] - base;
 
-  GV_CUDA(cudaMemcpyAsync(d_foff, foff.data(), foff.size() * sizeof(unsigned long long),
-                          cudaMemcpyHostToDevice, ctx->stream));
-  GV_CUDA(cudaMemcpyAsync(d_boff, box_frame_offsets, ((size_t)nframes + 1) * sizeof(int),
-                          cudaMemcpyHostToDevice, ctx->stream));
-  GV_CUDA(cudaMemcpyAsync(d_tprefix, tile_prefix.data(), tile_prefix.size() * sizeof(unsigned),
-                          cudaMemcpyHostToDevice, ctx->stream));
-  k_build_tiles<<<nframes, 128, 0, ctx->stream>>>(d_foff, d_boff, d_tprefix, nframes, tile_pts,
-                                                 d_tstart, d_tend, d_tbox);
-  GV_LAUNCH_CHECK();
+  if (!same) {
+    // the source vectors are context-owned, so no stream synchronisation is needed here
+    GV_CUDA(cudaMemcpyAsync(d_foff, foff.data(), foff.size() * sizeof(unsigned long long),
+                            cudaMemcpyHostToDevice, ctx->stream));
+    GV_CUDA(cudaMemcpyAsync(d_boff, ctx->c_boff.data(), ((size_t)nframes + 1) * sizeof(int),
+                            cudaMemcpyHostToDevice, ctx->stream));
+    GV_CUDA(cudaMemcpyAsync(d_tprefix, tile_prefix.data(), tile_prefix.size() * sizeof(unsigned),
+                            cudaMemcpyHostToDevice, ctx->stream));
+    k_build_tiles<<<nframes, 128, 0, ctx->stream>>>(d_foff, d_boff, d_tprefix, nframes, tile_pts,
+                                                   d_tstart, d_tend, d_tbox);
+    GV_LAUNCH_CHECK();
+    ctx->c_valid = true;
+  }
   float4 *d_f4 = nullptr;
   GV_TRY(upload_boxes(ctx, boxes, nboxes, boxes_on_device, &d_f4));
   // per-frame image-tile box masks
@@ -1331,9 +1354,6 @@ static int process_batch_impl(gv_ctx *ctx, const float *px, const float *py, con
   GV_LAUNCH_CHECK();
   a.masks = d_masks;
   a.tile_pts = tile_pts;
-  // host staging below reads foff/tile_prefix only on the host; the async copies above read
-  // pageable host vectors, so make sure they are consumed before the vectors die
-  GV_CUDA(cudaStreamSynchronize(ctx->stream));
 
   a.x = d_x;
   a.y = d_y;
