@@ -54,7 +54,7 @@ EXPORTS = [
     "gv_process_batch", "gv_process_batch_dev",
     "gv_grid_to_occupancy",
     "gv_nccl_unique_id", "gv_nccl_init", "gv_nccl_world", "gv_grid_finalize_multi",
-    "gv_ipc_export", "gv_ipc_import",
+    "gv_ipc_export", "gv_ipc_import", "gv_ipc_close",
 ]
 
 _lib = None

@@ -329,6 +329,9 @@ class Context:
         self._check(self._lib.gv_ipc_import(self._h, C.c_char_p(blobs), C.c_int(world), C.c_int(rank)),
                     "gv_ipc_import")
 
+    def ipc_close(self):
+        self._check(self._lib.gv_ipc_close(self._h), "gv_ipc_close")
+
     def nccl_init(self, unique_id: bytes, rank: int, world: int):
         assert len(unique_id) == 128
         self._check(self._lib.gv_nccl_init(self._h, C.c_char_p(unique_id), C.c_int(rank),

@@ -58,7 +58,7 @@ struct gv_ctx {
   unsigned long long *d_ends = nullptr;
   unsigned *d_list_count = nullptr;  // work-item counter of the raycast sweep
   SweepEntry *d_sweep = nullptr;     // sweep table for the current start cell
-  unsigned *d_sweep_prefix = nullptr;
+  unsigned *d_sweep_prefix = nullptr;  // [n_sweep+1] first work item of each entry
   int n_sweep = 0;
   unsigned n_sweep_items = 0;
   bool counts_dirty = false, ends_dirty = false;
@@ -90,6 +90,12 @@ struct gv_ctx {
   Peers<int32_t> peer_hit{}, peer_miss{};
   Peers<float> peer_lo{}, peer_occ{};
   int *d_barrier = nullptr;
+  // optional stage timing of gv_grid_finalize_multi ($GV_TIMING=1): events + accumulated ms
+  bool timing = false;
+  cudaEvent_t tev[8] = {};
+  int tev_n = 0;
+  double t_acc[8] = {};
+  long t_cnt = 0;
 
   int fail(int code, const char *fmt, ...)
   {
@@ -129,6 +135,25 @@ struct gv_ctx {
   } while (0)
 
 namespace {
+
+void stage_mark(gv_ctx *ctx, int i)
+{
+  if (!ctx->timing) return;
+  if (!ctx->tev[i]) cudaEventCreate(&ctx->tev[i]);
+  cudaEventRecord(ctx->tev[i], ctx->stream);
+  if (i + 1 > ctx->tev_n) ctx->tev_n = i + 1;
+}
+
+void stage_collect(gv_ctx *ctx)
+{
+  if (!ctx->timing || ctx->tev_n < 2) return;
+  cudaEventSynchronize(ctx->tev[ctx->tev_n - 1]);
+  for (int i = 0; i + 1 < ctx->tev_n; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->tev[i], ctx->tev[i + 1]) == cudaSuccess) ctx->t_acc[i] += ms;
+  }
+  ctx->t_cnt++;
+}
 
 int reserve(gv_ctx *ctx, int slot, size_t bytes, void **out)
 {
@@ -400,28 +425,30 @@ int accumulate_dev_impl(gv_ctx *ctx, const float *d_x, const float *d_y, const f
   return launch_points(ctx, false, true, a, blocks_for(n, a.tile_pts), 32);
 }
 
-int raycast_flush_impl(gv_ctx *ctx, unsigned rank, unsigned world, bool p2p_sweep = false)
+int raycast_flush_impl(gv_ctx *ctx, unsigned rank, unsigned world, bool p2p_gather = false)
 {
   if (!ctx->ends_dirty) return GV_OK;
   ctx->ends_dirty = false;
   if (!ctx->bin.origin_ok || ctx->n_sweep_items == 0) return GV_OK;  // nothing was binned
   GV_CUDA(cudaMemsetAsync(ctx->d_list_count, 0, sizeof(unsigned), ctx->stream));
   const unsigned nb = (unsigned)ctx->num_sms * 8u;
-  if (p2p_sweep)
-    k_raycast_sweep<true><<<nb, kThreads, 0, ctx->stream>>>(
-      ctx->d_ends, ctx->d_hit, ctx->d_miss, ctx->d_sweep, ctx->d_sweep_prefix, ctx->n_sweep,
-      ctx->n_sweep_items, ctx->bin.sx, ctx->bin.sy, ctx->g.nx, rank, world, ctx->d_list_count,
-      ctx->d_stats, ctx->peer_ends);
-  else
-    k_raycast_sweep<false><<<nb, kThreads, 0, ctx->stream>>>(
-      ctx->d_ends, ctx->d_hit, ctx->d_miss, ctx->d_sweep, ctx->d_sweep_prefix, ctx->n_sweep,
-      ctx->n_sweep_items, ctx->bin.sx, ctx->bin.sy, ctx->g.nx, rank, world, ctx->d_list_count,
-      ctx->d_stats, ctx->peer_ends);
+  if (p2p_gather) {
+    // fused all-reduce of the ends plane, restricted to the cells whose lines this rank walks
+    k_ends_gather<<<nb, kThreads, 0, ctx->stream>>>(ctx->d_ends, ctx->d_sweep, ctx->d_sweep_prefix,
+                                                   ctx->n_sweep, ctx->n_sweep_items, ctx->bin.sx,
+                                                   ctx->bin.sy, ctx->g.nx, rank, world, ctx->peer_ends);
+    GV_LAUNCH_CHECK();
+  }
+  k_raycast_sweep<<<nb, kThreads, 0, ctx->stream>>>(ctx->d_ends, ctx->d_hit, ctx->d_miss, ctx->d_sweep,
+                                                    ctx->d_sweep_prefix, ctx->n_sweep,
+                                                    ctx->n_sweep_items, ctx->bin.sx, ctx->bin.sy,
+                                                    ctx->g.nx, rank, world, world == 1 ? 1 : 0,
+                                                    ctx->d_list_count, ctx->d_stats);
   GV_LAUNCH_CHECK();
-  // NCCL multi-GPU path: this rank settled and cleared only the end cells of its own work
-  // items; the entries owned by the other ranks were handled there, drop them.  (The P2P sweep
-  // clears every rank's entries itself.)
-  if (world > 1 && !p2p_sweep)
+  // multi-GPU, NCCL path: the plane holds every rank's (all-reduced) entries but this rank
+  // walked only its own items: drop the rest.  In P2P mode the peers may still be gathering
+  // from this plane: the caller clears it after the next barrier instead.
+  if (world > 1 && !p2p_gather)
     GV_CUDA(cudaMemsetAsync(ctx->d_ends, 0, ctx->ncells * sizeof(unsigned long long), ctx->stream));
   ctx->counts_dirty = true;
   return GV_OK;
@@ -724,6 +751,7 @@ int gv_create(gv_ctx **out, int device)
     return GV_ERR_CUDA;
   }
   ctx->stream = ctx->own_stream;
+  ctx->timing = std::getenv("GV_TIMING") != nullptr;
   *out = ctx;
   return GV_OK;
 }
@@ -733,6 +761,14 @@ void gv_destroy(gv_ctx *ctx)
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
+  if (ctx->timing && ctx->t_cnt > 0 && ctx->rank == 0) {
+    std::fprintf(stderr, "[grid_vision_b200] finalize_multi stages (ms, mean of %ld, %s):", ctx->t_cnt,
+                 ctx->p2p ? "p2p" : "nccl");
+    for (int i = 0; i + 1 < ctx->tev_n; ++i) std::fprintf(stderr, " %.3f", ctx->t_acc[i] / ctx->t_cnt);
+    std::fprintf(stderr, "\n");
+  }
+  for (auto &e : ctx->tev)
+    if (e) cudaEventDestroy(e);
 #ifdef GV_WITH_NCCL
   if (ctx->comm) ncclCommDestroy(ctx->comm);
 #endif
@@ -1537,26 +1573,39 @@ int gv_grid_finalize_multi(gv_ctx *ctx, int32_t k_decay, const double *corners, 
       GV_NCCL(ncclAllReduce(ctx->d_barrier, ctx->d_barrier, 1, ncclInt32, ncclSum, ctx->comm, ctx->stream));
       return GV_OK;
     };
+    stage_mark(ctx, 0);
     GV_TRY(barrier());  // every rank has finished binning into its ends plane
+    stage_mark(ctx, 1);
     ctx->ends_dirty = true;
-    GV_TRY(raycast_flush_impl(ctx, rank, world, true));  // sums + clears all ranks' ends entries
-    GV_TRY(barrier());  // every rank's partial hit/miss planes are complete
+    GV_TRY(raycast_flush_impl(ctx, rank, world, true));  // gathers its cells from all ranks, walks
+    stage_mark(ctx, 2);
+    GV_TRY(barrier());  // every rank's partial hit/miss planes are complete, gathers are done
+    GV_CUDA(cudaMemsetAsync(ctx->d_ends, 0, ctx->ncells * sizeof(unsigned long long), ctx->stream));
+    stage_mark(ctx, 3);
     int4 *d_rects = nullptr;
     GV_TRY(footprint_rects(ctx, corners, nullptr, nfoot, 0, &d_rects));
     const size_t c0 = (size_t)rank * slab;
     const size_t c1 = c0 + slab < ctx->ncells ? c0 + slab : ctx->ncells;
     if (c1 > c0) GV_TRY(finalize_slab(ctx, k_decay, d_rects, nfoot, c0, c1 - c0, true, true));
-    GV_TRY(barrier());  // every slab has been written into every rank's grid, counts cleared
+    stage_mark(ctx, 4);
+    GV_TRY(barrier());  // every slab has been written into every rank's grid, counts consumed
+    GV_CUDA(cudaMemsetAsync(ctx->d_hit, 0, ctx->ncells * sizeof(int32_t), ctx->stream));
+    GV_CUDA(cudaMemsetAsync(ctx->d_miss, 0, ctx->ncells * sizeof(int32_t), ctx->stream));
+    stage_mark(ctx, 5);
+    stage_collect(ctx);
     ctx->counts_dirty = false;
     ctx->beams_bound = 0;
     return GV_OK;
   }
   // 1. every rank learns every rank's binned beams: exact u64 sum of the (total,hit) plane
+  stage_mark(ctx, 0);
   GV_NCCL(ncclAllReduce(ctx->d_ends, ctx->d_ends, ctx->ncells, ncclUint64, ncclSum, ctx->comm,
                         ctx->stream));
   // 2. the de-duplicated raycast is split by end cell (lin % world), partial planes result
+  stage_mark(ctx, 1);
   ctx->ends_dirty = true;  // a rank with no local beams still owns a share of the lines
   GV_TRY(raycast_flush_impl(ctx, rank, world));
+  stage_mark(ctx, 2);
   // 3. exact int32 sums of the partial planes, scattered by slab
   GV_NCCL(ncclGroupStart());
   GV_NCCL(ncclReduceScatter(ctx->d_hit, ctx->d_hit + (size_t)rank * slab, slab, ncclInt32, ncclSum,
@@ -1564,6 +1613,7 @@ int gv_grid_finalize_multi(gv_ctx *ctx, int32_t k_decay, const double *corners, 
   GV_NCCL(ncclReduceScatter(ctx->d_miss, ctx->d_miss + (size_t)rank * slab, slab, ncclInt32,
                             ncclSum, ctx->comm, ctx->stream));
   GV_NCCL(ncclGroupEnd());
+  stage_mark(ctx, 3);
   // 4. finalise the local slab
   int4 *d_rects = nullptr;
   GV_TRY(footprint_rects(ctx, corners, nullptr, nfoot, 0, &d_rects));
@@ -1573,11 +1623,14 @@ int gv_grid_finalize_multi(gv_ctx *ctx, int32_t k_decay, const double *corners, 
   const size_t padded = ctx->ncells + kPlanePad;
   GV_CUDA(cudaMemsetAsync(ctx->d_hit, 0, padded * sizeof(int32_t), ctx->stream));
   GV_CUDA(cudaMemsetAsync(ctx->d_miss, 0, padded * sizeof(int32_t), ctx->stream));
+  stage_mark(ctx, 4);
   // 5. every rank ends with the full grid
   GV_NCCL(ncclGroupStart());
   GV_NCCL(ncclAllGather(ctx->d_lo + c0, ctx->d_lo, slab, ncclFloat32, ctx->comm, ctx->stream));
   GV_NCCL(ncclAllGather(ctx->d_occ + c0, ctx->d_occ, slab, ncclFloat32, ctx->comm, ctx->stream));
   GV_NCCL(ncclGroupEnd());
+  stage_mark(ctx, 5);
+  stage_collect(ctx);
   ctx->counts_dirty = false;
   ctx->beams_bound = 0;
   return GV_OK;
@@ -1644,6 +1697,15 @@ int gv_ipc_import(gv_ctx *ctx, const void *blobs, int world, int rank)
     ctx->peer_lo.p[r] = static_cast<float *>(q[3]);
     ctx->peer_occ.p[r] = static_cast<float *>(q[4]);
   }
+  return GV_OK;
+}
+
+int gv_ipc_close(gv_ctx *ctx)
+{
+  if (!ctx) return GV_ERR_INVALID;
+  GV_CUDA(cudaSetDevice(ctx->device));
+  GV_CUDA(cudaStreamSynchronize(ctx->stream));
+  close_peers(ctx);
   return GV_OK;
 }
 

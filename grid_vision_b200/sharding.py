@@ -69,6 +69,5 @@ def enable_p2p(ctx, device="cuda") -> bool:
     t = torch.tensor([ok], dtype=torch.int32, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if int(t.item()) == 0 and ok:
-        # someone failed: every rank must use the same path
-        raise RuntimeError("inconsistent peer-memory mapping across ranks")
+        ctx.ipc_close()  # another rank could not map its peers: every rank must use the same path
     return bool(int(t.item()))

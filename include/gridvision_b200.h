@@ -250,6 +250,8 @@ GV_API int gv_grid_finalize_multi(gv_ctx *ctx, int32_t k_decay, const double *co
 #define GV_IPC_BLOB_BYTES 320
 GV_API int gv_ipc_export(gv_ctx *ctx, void *blob_out);
 GV_API int gv_ipc_import(gv_ctx *ctx, const void *blobs, int world, int rank);
+/* unmap the peers again: gv_grid_finalize_multi goes back to the NCCL collectives */
+GV_API int gv_ipc_close(gv_ctx *ctx);
 
 #ifdef __cplusplus
 }

@@ -609,6 +609,120 @@ void gvo_finalize(gvo_grid *g, int32_t k_decay, const double *corners, int nfoot
 }
 
 /* ------------------------------------------------------------------------- */
+/* N2  radius outlier removal + PCA box (src/cloud_detections.cpp:140-247)    */
+/* ------------------------------------------------------------------------- */
+
+int32_t gvo_radius_outlier_keep(const float *x, const float *y, const float *z, size_t n,
+                                double radius, int32_t min_neighbors, uint8_t *keep)
+{
+  /* :150-154 RadiusOutlierRemoval: setRadiusSearch(0.4), setMinNeighborsInRadius(10).
+   * pcl::KdTreeFLANN::radiusSearch hands FLANN static_cast<float>(radius * radius); FLANN's
+   * RadiusResultSet keeps dist < radius2 (strict); k includes the query; k <= min_pts removes. */
+  const float r2 = (float)(radius * radius);
+  int32_t kept = 0;
+  for (size_t i = 0; i < n; ++i) {
+    int32_t k = 0;
+    for (size_t j = 0; j < n; ++j) {
+      const float dx = x[j] - x[i], dy = y[j] - y[i], dz = z[j] - z[i];
+      const float dxx = dx * dx, dyy = dy * dy, dzz = dz * dz;
+      const float s = dxx + dyy;
+      const float d2 = s + dzz;
+      if (d2 < r2) ++k;
+    }
+    keep[i] = k > min_neighbors;
+    kept += keep[i];
+  }
+  return kept;
+}
+
+void gvo_bbox_pose(const float *x, const float *y, const float *z, size_t n, gvo_lshape *out)
+{
+  memset(out, 0, sizeof(*out));
+  out->qw = 1.0;
+  if (n == 0) return;
+  uint8_t *keep = (uint8_t *)malloc(n);
+  const int32_t m = gvo_radius_outlier_keep(x, y, z, n, 0.4, 10, keep);
+  out->kept = m;
+  if (m == 0) { /* :201-202 if(data.empty()) continue; */
+    free(keep);
+    return;
+  }
+  /* :157-158 compute3DCentroid (float accumulation in input order) */
+  float cy = 0.0f;
+  double sz = 0, sx = 0;
+  for (size_t i = 0; i < n; ++i)
+    if (keep[i]) {
+      cy = cy + y[i];
+      sz += (double)z[i];
+      sx += (double)x[i];
+    }
+  out->centroid_y = cy / (float)m;
+  /* :189-191 cv::PCA(data, Mat(), DATA_AS_ROW) on rows (z, x) */
+  const double mz = sz / m, mx = sx / m;
+  double czz = 0, czx = 0, cxx = 0;
+  for (size_t i = 0; i < n; ++i)
+    if (keep[i]) {
+      const double dz = (double)z[i] - mz, dx = (double)x[i] - mx;
+      czz += dz * dz;
+      czx += dz * dx;
+      cxx += dx * dx;
+    }
+  czz /= m;
+  czx /= m;
+  cxx /= m;
+  /* symmetric 2x2 eigen decomposition, larger eigenvalue first */
+  const double tr = czz + cxx, df = czz - cxx;
+  const double rad = sqrt(df * df + 4.0 * czx * czx);
+  const double l1 = 0.5 * (tr + rad);
+  double vz, vx;
+  if (fabs(czx) > 1e-300) {
+    vz = l1 - cxx;
+    vx = czx;
+  } else if (czz >= cxx) {
+    vz = 1.0;
+    vx = 0.0;
+  } else {
+    vz = 0.0;
+    vx = 1.0;
+  }
+  const double nv = sqrt(vz * vz + vx * vx);
+  vz /= nv;
+  vx /= nv;
+  if (vz < 0 || (vz == 0 && vx < 0)) { /* sign convention of THIS restatement: major.z >= 0 */
+    vz = -vz;
+    vx = -vx;
+  }
+  out->mean_z = (float)mz;
+  out->mean_x = (float)mx;
+  out->major_z = (float)vz;
+  out->major_x = (float)vx;
+  out->minor_z = (float)(-vx); /* orthogonal complement */
+  out->minor_x = (float)vz;
+  /* :204-222 extents along the axes, float like the reference's cv::Point2f arithmetic */
+  float minL = 3.402823466e+38f, maxL = -3.402823466e+38f, minW = minL, maxW = maxL;
+  for (size_t i = 0; i < n; ++i)
+    if (keep[i]) {
+      const float dz = z[i] - out->mean_z, dx = x[i] - out->mean_x;
+      const float pL = dz * out->major_z + dx * out->major_x;
+      const float pW = dz * out->minor_z + dx * out->minor_x;
+      if (pL < minL) minL = pL;
+      if (pL > maxL) maxL = pL;
+      if (pW < minW) minW = pW;
+      if (pW > maxW) maxW = pW;
+    }
+  out->length = maxL - minL;
+  out->width = maxW - minW;
+  /* :232 angle in degrees; :246-247 q.setRPY(0, -angle, 0) (degrees passed as radians: kept) */
+  out->angle_deg = atan2f(out->major_x, out->major_z) * 180.0f / 3.14159265358979323846f;
+  const double hp = -(double)out->angle_deg * 0.5;
+  out->qx = 0.0;
+  out->qy = sin(hp);
+  out->qz = 0.0;
+  out->qw = cos(hp);
+  free(keep);
+}
+
+/* ------------------------------------------------------------------------- */
 /* N3  nav_msgs/OccupancyGrid cell conversion (grid_map_ros toOccupancyGrid)  */
 /* ------------------------------------------------------------------------- */
 

@@ -158,6 +158,35 @@ int32_t gvo_bresenham_cells(int32_t sx, int32_t sy, int32_t ex, int32_t ey, int3
  * hit = miss = 0.  corners: nfoot x 4 x (x,y) doubles (may be NULL when nfoot==0). */
 void gvo_finalize(gvo_grid *g, int32_t k_decay, const double *corners, int nfoot);
 
+/* N2 (next row): cloud_detections::bboxPoseEstimation + computePCABoundingBox
+ * (src/cloud_detections.cpp:140-247) for ONE per-box cloud in the camera frame.
+ *   1. pcl::RadiusOutlierRemoval(r = 0.4, min neighbours 10): keep point i iff the number of
+ *      points j (itself included) with |p_j - p_i|^2 < (float)(0.4*0.4) exceeds 10; order kept.
+ *      (PCL / FLANN conventions RECALLED FROM UPSTREAM: k counts the query point, k <= min_pts
+ *      removes, FLANN's radius test is strict on the squared float distance.)
+ *   2. pcl::compute3DCentroid -> only centroid.y is used (:209)
+ *   3. cv::PCA on the N x 2 float rows (z, x): mean, 2x2 covariance, eigenvectors by descending
+ *      eigenvalue (closed form here; OpenCV's Jacobi agrees to rounding, eigenvector signs are
+ *      arbitrary in both)
+ *   4. extents of (pt - mean) along the two axes -> length, width (:224-237)
+ *   5. pose.position = (mean_x, centroid_y, mean_z); angle = atan2(major.y, major.x) in DEGREES,
+ *      fed to setRPY(0, -angle, 0) as if it were radians (:246,:254-255: a reference quirk, kept).
+ * Returns the number of points kept; 0 means the box is skipped (:201-202 data.empty()). */
+typedef struct {
+  int32_t kept;
+  float centroid_y;            /* pose.position.y            */
+  float mean_z, mean_x;        /* PCA mean (center.x, center.y): pose.position.z / .x */
+  float major_z, major_x;      /* first eigenvector (row 0)  */
+  float minor_z, minor_x;      /* second eigenvector (row 1) */
+  float length, width;
+  float angle_deg;
+  double qx, qy, qz, qw;       /* tf2::Quaternion::setRPY(0, -angle_deg, 0) */
+} gvo_lshape;
+
+int32_t gvo_radius_outlier_keep(const float *x, const float *y, const float *z, size_t n,
+                                double radius, int32_t min_neighbors, uint8_t *keep);
+void gvo_bbox_pose(const float *x, const float *y, const float *z, size_t n, gvo_lshape *out);
+
 /* N3 (next row): grid_map_ros toOccupancyGrid(layer "occupancy", 0, 1) cell conversion
  * into nav_msgs/OccupancyGrid data order. */
 void gvo_to_occupancy_grid(const gvo_grid *g, int8_t *data);

@@ -46,6 +46,14 @@ class _Grid(C.Structure):
                 ("hit", C.POINTER(C.c_int32)), ("miss", C.POINTER(C.c_int32))]
 
 
+class LShape(C.Structure):
+    _fields_ = [("kept", C.c_int32), ("centroid_y", C.c_float), ("mean_z", C.c_float),
+                ("mean_x", C.c_float), ("major_z", C.c_float), ("major_x", C.c_float),
+                ("minor_z", C.c_float), ("minor_x", C.c_float), ("length", C.c_float),
+                ("width", C.c_float), ("angle_deg", C.c_float), ("qx", C.c_double),
+                ("qy", C.c_double), ("qz", C.c_double), ("qw", C.c_double)]
+
+
 class _AccumParams(C.Structure):
     _fields_ = [("occ_mode", C.c_int32), ("use_z_gate", C.c_int32),
                 ("z_min", C.c_float), ("z_max", C.c_float), ("r_max", C.c_double)]
@@ -164,6 +172,23 @@ def bresenham_cells(sx, sy, ex, ey):
     m = lib().gvo_bresenham_cells(C.c_int32(sx), C.c_int32(sy), C.c_int32(ex), C.c_int32(ey),
                                   _p(out, C.c_int32), C.c_int32(n))
     assert m == n
+    return out
+
+
+def radius_outlier_keep(x, y, z, radius=0.4, min_neighbors=10):
+    x, y, z = _f32(x), _f32(y), _f32(z)
+    keep = np.zeros(x.size, np.uint8)
+    lib().gvo_radius_outlier_keep(_p(x, C.c_float), _p(y, C.c_float), _p(z, C.c_float),
+                                  C.c_size_t(x.size), C.c_double(radius), C.c_int32(min_neighbors),
+                                  _p(keep, C.c_uint8))
+    return keep.astype(bool)
+
+
+def bbox_pose(x, y, z) -> LShape:
+    x, y, z = _f32(x), _f32(y), _f32(z)
+    out = LShape()
+    lib().gvo_bbox_pose(_p(x, C.c_float), _p(y, C.c_float), _p(z, C.c_float), C.c_size_t(x.size),
+                        C.byref(out))
     return out
 
 
