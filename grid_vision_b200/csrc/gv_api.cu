@@ -31,7 +31,7 @@ enum {
   S_X, S_Y, S_Z, S_AOS, S_LAB, S_PIX, S_UV, S_BOX_RAW, S_BOX_F4, S_FRAME_OFF, S_BOX_OFF,
   S_TILE_PREFIX, S_TILE_START, S_TILE_END, S_TILE_BOX, S_CELL, S_FLAGS, S_FOOT_IN, S_FOOT_LAB,
   S_RECT, S_SMALL, S_OX, S_OY, S_OZ, S_SCAN0, S_SCAN1, S_SCAN2, S_SCAN3, S_UVZ, S_INDICES,
-  S_LABELS_IN, S_MASKS, S_SET_OFF, S_SWEEP, S_SWEEP_PREFIX, S_COUNT
+  S_LABELS_IN, S_MASKS, S_SET_OFF, S_SWEEP, S_SWEEP_PREFIX, S_BATCH_ENTRY, S_BATCH_MI, S_BATCH_W, S_COUNT
 };
 
 constexpr size_t kPlanePad = 4096;  // slack cells so multi-GPU slabs can be equal-sized
@@ -430,8 +430,15 @@ int raycast_flush_impl(gv_ctx *ctx, unsigned rank, unsigned world, bool p2p_gath
   if (!ctx->ends_dirty) return GV_OK;
   ctx->ends_dirty = false;
   if (!ctx->bin.origin_ok || ctx->n_sweep_items == 0) return GV_OK;  // nothing was binned
-  GV_CUDA(cudaMemsetAsync(ctx->d_list_count, 0, sizeof(unsigned), ctx->stream));
+  GV_CUDA(cudaMemsetAsync(ctx->d_list_count, 0, 4 * sizeof(unsigned), ctx->stream));
   const unsigned nb = (unsigned)ctx->num_sms * 8u;
+  // batch list: every non-empty cell once, each span padded to a multiple of 32
+  const size_t max_batches = ctx->ncells / 32 + (size_t)ctx->n_sweep_items + 1;
+  int *d_bentry, *d_bmi;
+  unsigned *d_bw;
+  GV_TRY(reserve_t(ctx, S_BATCH_ENTRY, max_batches, &d_bentry));
+  GV_TRY(reserve_t(ctx, S_BATCH_MI, max_batches * 32, &d_bmi));
+  GV_TRY(reserve_t(ctx, S_BATCH_W, max_batches * 32, &d_bw));
   if (p2p_gather) {
     // fused all-reduce of the ends plane, restricted to the cells whose lines this rank walks
     k_ends_gather<<<nb, kThreads, 0, ctx->stream>>>(ctx->d_ends, ctx->d_sweep, ctx->d_sweep_prefix,
@@ -439,11 +446,16 @@ int raycast_flush_impl(gv_ctx *ctx, unsigned rank, unsigned world, bool p2p_gath
                                                    ctx->bin.sy, ctx->g.nx, rank, world, ctx->peer_ends);
     GV_LAUNCH_CHECK();
   }
-  k_raycast_sweep<<<nb, kThreads, 0, ctx->stream>>>(ctx->d_ends, ctx->d_hit, ctx->d_miss, ctx->d_sweep,
+  k_sweep_compact<<<nb, kThreads, 0, ctx->stream>>>(ctx->d_ends, ctx->d_hit, ctx->d_miss, ctx->d_sweep,
                                                     ctx->d_sweep_prefix, ctx->n_sweep,
                                                     ctx->n_sweep_items, ctx->bin.sx, ctx->bin.sy,
                                                     ctx->g.nx, rank, world, world == 1 ? 1 : 0,
-                                                    ctx->d_list_count, ctx->d_stats);
+                                                    ctx->d_list_count, d_bentry, d_bmi, d_bw,
+                                                    ctx->d_stats);
+  GV_LAUNCH_CHECK();
+  k_sweep_walk<<<nb, kThreads, 0, ctx->stream>>>(ctx->d_miss, ctx->d_sweep, ctx->d_list_count, d_bentry,
+                                                 d_bmi, d_bw, ctx->bin.sx, ctx->bin.sy, ctx->g.nx,
+                                                 ctx->d_stats);
   GV_LAUNCH_CHECK();
   // multi-GPU, NCCL path: the plane holds every rank's (all-reduced) entries but this rank
   // walked only its own items: drop the rest.  In P2P mode the peers may still be gathering
@@ -490,7 +502,7 @@ int build_sweep_table(gv_ctx *ctx)
   unsigned long long items = 0;
   for (size_t i = 0; i < ent.size(); ++i) {
     prefix[i] = (unsigned)items;
-    items += (unsigned long long)(ent[i].m1 - ent[i].m0) / 32ull + 1ull;
+    items += (unsigned long long)(ent[i].m1 - ent[i].m0) / (unsigned long long)kSpanCells + 1ull;
   }
   GV_REQUIRE(items < 4294967295ull, GV_ERR_INVALID, "sweep table too large");
   prefix[ent.size()] = (unsigned)items;
@@ -744,7 +756,7 @@ int gv_create(gv_ctx **out, int device)
       cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaMalloc(&ctx->d_stats, 4 * sizeof(unsigned long long)) != cudaSuccess ||
-      cudaMalloc(&ctx->d_list_count, sizeof(unsigned)) != cudaSuccess ||
+      cudaMalloc(&ctx->d_list_count, 4 * sizeof(unsigned)) != cudaSuccess ||
       cudaMemset(ctx->d_stats, 0, 4 * sizeof(unsigned long long)) != cudaSuccess) {
     cudaGetLastError();
     gv_destroy(ctx);

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Full-size bench + ncu launch list (+ one --set full capture of the top kernels). Logs -> gpurun_out/.
 mkdir -p gpurun_out
-BENCH_ARGS="--frames ${PFRAMES:-512} --steps 2 --warmup 1 --no-e2e --no-cpu --no-extra"
+BENCH_ARGS="--frames ${PFRAMES:-4096} --steps 2 --warmup 1 --no-e2e --no-cpu --no-extra"
 timeout 900 python bench.py > gpurun_out/bench_full.log 2>&1; echo "bench_full exit $?"
 tail -1 gpurun_out/bench_full.log
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.log 2>&1; echo "bench_ref exit $?"
@@ -12,7 +12,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base fun
 echo "ncu list exit $?"
 if [ "${FULL:-1}" = "1" ]; then
 python bench.py $BENCH_ARGS > gpurun_out/plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on --kernel-name-base function --kernel-name regex:'^k_(points|raycast_sweep|finalize)' -s 3 -c 3 \
+ncu --set full --clock-control none --import-source on --kernel-name-base function --kernel-name regex:'^k_(points|sweep_compact|sweep_walk|finalize)' -s 4 -c 4 \
     -o gpurun_out/prof -f python bench.py $BENCH_ARGS > gpurun_out/ncu_full.log 2>&1
 echo "ncu full exit $?"
 fi
