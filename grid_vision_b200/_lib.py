@@ -33,6 +33,14 @@ class GridDesc(C.Structure):
                 ("pos_x", C.c_double), ("pos_y", C.c_double)]
 
 
+class LShape(C.Structure):
+    _fields_ = [("kept", C.c_int32), ("centroid_y", C.c_float), ("mean_z", C.c_float),
+                ("mean_x", C.c_float), ("major_z", C.c_float), ("major_x", C.c_float),
+                ("minor_z", C.c_float), ("minor_x", C.c_float), ("length", C.c_float),
+                ("width", C.c_float), ("angle_deg", C.c_float), ("qx", C.c_double),
+                ("qy", C.c_double), ("qz", C.c_double), ("qw", C.c_double)]
+
+
 class Stats(C.Structure):
     _fields_ = [("beams", C.c_uint64), ("cells_logical", C.c_uint64),
                 ("cells_physical", C.c_uint64), ("distinct_ends", C.c_uint64),
@@ -44,7 +52,7 @@ EXPORTS = [
     "gv_version", "gv_status_string", "gv_create", "gv_destroy", "gv_last_error",
     "gv_synchronize", "gv_stream", "gv_set_stream", "gv_get_stats",
     "gv_set_cameras", "gv_fuse", "gv_fuse_aos32", "gv_fuse_dev", "gv_transform_points",
-    "gv_project_kdtree", "gv_partition_by_label",
+    "gv_project_kdtree", "gv_partition_by_label", "gv_segment_ground", "gv_bbox_pose",
     "gv_grid_init_reference", "gv_grid_init", "gv_grid_get_desc", "gv_grid_reset",
     "gv_grid_upload", "gv_grid_download", "gv_grid_counts_download", "gv_grid_layers_dev",
     "gv_grid_get_index",

@@ -165,6 +165,28 @@ class Context:
                     "gv_partition_by_label")
         return idx[:int(off[nboxes])].copy(), off
 
+    def segment_ground(self, x, y, z, threshold=0.04, seed=12345, n_hyp=256):
+        """N1 -> (xyz kept [3,m] float32, plane[4], found)."""
+        x, y, z = (_np(a, np.float32) for a in (x, y, z))
+        n = x.size
+        out = np.empty((3, max(n, 1)), np.float32)
+        m, found = C.c_size_t(0), C.c_int(0)
+        plane = np.zeros(4, np.float32)
+        self._check(self._lib.gv_segment_ground(
+            self._h, _ptr(x), _ptr(y), _ptr(z), C.c_size_t(n), C.c_float(threshold), C.c_uint32(seed),
+            C.c_int(n_hyp), C.c_void_p(out[0].ctypes.data), C.c_void_p(out[1].ctypes.data),
+            C.c_void_p(out[2].ctypes.data), C.byref(m), _ptr(plane), C.byref(found)), "gv_segment_ground")
+        return out[:, :m.value].copy(), plane, bool(found.value)
+
+    def bbox_pose(self, x, y, z, labels, nboxes):
+        """N2: radius-outlier filter + PCA box per label -> list of _lib.LShape (kept == 0: skipped)."""
+        x, y, z = (_np(a, np.float32) for a in (x, y, z))
+        labels = _np(labels, np.int16)
+        out = (_lib.LShape * max(nboxes, 1))()
+        self._check(self._lib.gv_bbox_pose(self._h, _ptr(x), _ptr(y), _ptr(z), C.c_size_t(x.size),
+                                           _ptr(labels), C.c_int(nboxes), out), "gv_bbox_pose")
+        return list(out)[:nboxes]
+
     # ------------------------------------------------------------------ grid
     def grid_init(self, length_x, length_y, resolution, pos_x=0.0, pos_y=0.0):
         self._check(self._lib.gv_grid_init(self._h, C.c_double(length_x), C.c_double(length_y),

@@ -31,7 +31,7 @@ enum {
   S_X, S_Y, S_Z, S_AOS, S_LAB, S_PIX, S_UV, S_BOX_RAW, S_BOX_F4, S_FRAME_OFF, S_BOX_OFF,
   S_TILE_PREFIX, S_TILE_START, S_TILE_END, S_TILE_BOX, S_CELL, S_FLAGS, S_FOOT_IN, S_FOOT_LAB,
   S_RECT, S_SMALL, S_OX, S_OY, S_OZ, S_SCAN0, S_SCAN1, S_SCAN2, S_SCAN3, S_UVZ, S_INDICES,
-  S_LABELS_IN, S_MASKS, S_SET_OFF, S_SWEEP, S_SWEEP_PREFIX, S_BATCH_ENTRY, S_BATCH_MI, S_BATCH_W, S_COUNT
+  S_LABELS_IN, S_MASKS, S_SET_OFF, S_SWEEP, S_SWEEP_PREFIX, S_BATCH_ENTRY, S_BATCH_MI, S_BATCH_W, S_N2_TAB, S_N2_KEEP, S_N2_OUT, S_N2_OFF, S_N1_PLANES, S_N1_VALID, S_N1_SCORES, S_N1_STATE, S_COUNT
 };
 
 constexpr size_t kPlanePad = 4096;  // slack cells so multi-GPU slabs can be equal-sized
@@ -1062,6 +1062,149 @@ int gv_partition_by_label(gv_ctx *ctx, const int16_t *labels, size_t n, int nbox
   if (h_off[nboxes])
     GV_CUDA(cudaMemcpyAsync(indices_out, d_idx, (size_t)h_off[nboxes] * sizeof(unsigned),
                             cudaMemcpyDeviceToHost, ctx->stream));
+  GV_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GV_OK;
+}
+
+// N1: RANSAC ground-plane removal (ref: src/cloud_detections.cpp:105-138)
+int gv_segment_ground(gv_ctx *ctx, const float *x, const float *y, const float *z, size_t n,
+                      float threshold, uint32_t seed, int n_hyp, float *ox, float *oy, float *oz,
+                      size_t *m_out, float *plane_out, int *found_out)
+{
+  if (!ctx) return GV_ERR_INVALID;
+  GV_CUDA(cudaSetDevice(ctx->device));
+  GV_REQUIRE(m_out != nullptr, GV_ERR_INVALID, "m_out is NULL");
+  GV_REQUIRE(n_hyp >= 1 && n_hyp <= kMaxHyp, GV_ERR_INVALID, "n_hyp %d not in [1,%d]", n_hyp, kMaxHyp);
+  GV_REQUIRE(n < 4294967296ull, GV_ERR_INVALID, "n too large");
+  *m_out = 0;
+  if (found_out) *found_out = 0;
+  if (plane_out) plane_out[0] = plane_out[1] = plane_out[2] = plane_out[3] = 0.0f;
+  if (n < 3) return GV_OK;  // no planar model: the reference returns an empty cloud
+  GV_REQUIRE(ox && oy && oz, GV_ERR_INVALID, "output planes are NULL");
+  float *d_x, *d_y, *d_z, *d_ox, *d_oy, *d_oz;
+  GV_TRY(upload_cloud(ctx, x, y, z, n, &d_x, &d_y, &d_z));
+  float4 *d_planes;
+  int *d_valid, *d_scores;
+  GroundState *d_st;
+  unsigned *d_cnt;
+  const unsigned nb = blocks_for(n, kThreads);
+  GV_TRY(reserve_t(ctx, S_N1_PLANES, (size_t)n_hyp, &d_planes));
+  GV_TRY(reserve_t(ctx, S_N1_VALID, (size_t)n_hyp, &d_valid));
+  GV_TRY(reserve_t(ctx, S_N1_SCORES, (size_t)n_hyp, &d_scores));
+  GV_TRY(reserve_t(ctx, S_N1_STATE, 1, &d_st));
+  GV_TRY(reserve_t(ctx, S_SCAN0, (size_t)nb + 1, &d_cnt));
+  GV_TRY(reserve_t(ctx, S_OX, n, &d_ox));
+  GV_TRY(reserve_t(ctx, S_OY, n, &d_oy));
+  GV_TRY(reserve_t(ctx, S_OZ, n, &d_oz));
+  GV_CUDA(cudaMemsetAsync(d_scores, 0, (size_t)n_hyp * sizeof(int), ctx->stream));
+  k_n1_hypotheses<<<blocks_for(n_hyp, 128), 128, 0, ctx->stream>>>(d_x, d_y, d_z, (unsigned)n, seed, n_hyp,
+                                                                   d_planes, d_valid);
+  GV_LAUNCH_CHECK();
+  const unsigned sb = (unsigned)ctx->num_sms * 4u;
+  k_n1_score<<<sb, kThreads, 0, ctx->stream>>>(d_x, d_y, d_z, n, d_planes, d_valid, n_hyp, threshold, d_scores);
+  GV_LAUNCH_CHECK();
+  k_n1_best<<<1, 32, 0, ctx->stream>>>(d_planes, d_scores, n_hyp, d_st);
+  GV_LAUNCH_CHECK();
+  for (int pass = 0; pass < 2; ++pass) {
+    k_n1_moments<<<sb, kThreads, 0, ctx->stream>>>(d_x, d_y, d_z, n, threshold, pass, d_st);
+    GV_LAUNCH_CHECK();
+  }
+  k_n1_refine<<<1, 1, 0, ctx->stream>>>(d_st);
+  GV_LAUNCH_CHECK();
+  GV_CUDA(cudaMemsetAsync(d_cnt + nb, 0, sizeof(unsigned), ctx->stream));
+  k_n1_count<<<nb, kThreads, 0, ctx->stream>>>(d_x, d_y, d_z, n, threshold, d_st, d_cnt, nullptr);
+  GV_LAUNCH_CHECK();
+  GV_TRY(scan_u32(ctx, d_cnt, (unsigned long long)nb + 1, 0));
+  k_n1_scatter<<<nb, kThreads, 0, ctx->stream>>>(d_x, d_y, d_z, n, threshold, d_st, d_cnt, d_ox, d_oy, d_oz);
+  GV_LAUNCH_CHECK();
+  GroundState st;
+  unsigned total = 0;
+  GV_CUDA(cudaMemcpyAsync(&st, d_st, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
+  GV_CUDA(cudaMemcpyAsync(&total, d_cnt + nb, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+  GV_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (!st.found) return GV_OK;  // ref: :122-126 empty cloud
+  if (found_out) *found_out = 1;
+  if (plane_out) {
+    plane_out[0] = st.plane.x; plane_out[1] = st.plane.y; plane_out[2] = st.plane.z; plane_out[3] = st.plane.w;
+  }
+  if (total) {
+    GV_CUDA(cudaMemcpyAsync(ox, d_ox, (size_t)total * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    GV_CUDA(cudaMemcpyAsync(oy, d_oy, (size_t)total * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    GV_CUDA(cudaMemcpyAsync(oz, d_oz, (size_t)total * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    GV_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  *m_out = total;
+  return GV_OK;
+}
+
+// N2: radius-outlier filter + PCA box per label (ref: src/cloud_detections.cpp:140-247)
+int gv_bbox_pose(gv_ctx *ctx, const float *x, const float *y, const float *z, size_t n,
+                 const int16_t *labels, int nboxes, gv_lshape *out)
+{
+  if (!ctx) return GV_ERR_INVALID;
+  GV_CUDA(cudaSetDevice(ctx->device));
+  static_assert(sizeof(gv_lshape) == sizeof(LShapeDev), "gv_lshape layout");
+  GV_REQUIRE(nboxes >= 0 && nboxes <= 1024, GV_ERR_INVALID, "nboxes %d not in [0,1024]", nboxes);
+  GV_REQUIRE(n < 4294967296ull, GV_ERR_INVALID, "n too large for 32-bit indices");
+  if (nboxes == 0) return GV_OK;
+  GV_REQUIRE(out != nullptr, GV_ERR_INVALID, "out is NULL");
+  for (int b = 0; b < nboxes; ++b) {
+    memset(&out[b], 0, sizeof(gv_lshape));
+    out[b].qw = 1.0;
+  }
+  if (n == 0) return GV_OK;
+  GV_REQUIRE(labels != nullptr, GV_ERR_INVALID, "labels is NULL");
+  // stable partition of point indices by label, on the device (same kernels as
+  // gv_partition_by_label), offsets come back to size the launches
+  float *d_x, *d_y, *d_z;
+  GV_TRY(upload_cloud(ctx, x, y, z, n, &d_x, &d_y, &d_z));
+  const unsigned nb = blocks_for(n, kThreads);
+  const unsigned long long hn = (unsigned long long)nboxes * nb;
+  int16_t *d_lab;
+  unsigned *d_hist, *d_idx;
+  GV_TRY(reserve_t(ctx, S_LABELS_IN, n, &d_lab));
+  GV_TRY(reserve_t(ctx, S_SCAN0, (size_t)hn + 1, &d_hist));
+  GV_TRY(reserve_t(ctx, S_INDICES, n, &d_idx));
+  GV_CUDA(cudaMemcpyAsync(d_lab, labels, n * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
+  GV_CUDA(cudaMemsetAsync(d_hist + hn, 0, sizeof(unsigned), ctx->stream));
+  k_label_hist<<<nb, kThreads, (size_t)nboxes * sizeof(unsigned), ctx->stream>>>(d_lab, n, nboxes, nb, d_hist);
+  GV_LAUNCH_CHECK();
+  GV_TRY(scan_u32(ctx, d_hist, hn + 1, 0));
+  k_label_scatter<<<nb, kThreads, (size_t)nboxes * (kThreads / 32) * sizeof(unsigned), ctx->stream>>>(
+    d_lab, n, nboxes, nb, d_hist, d_idx);
+  GV_LAUNCH_CHECK();
+  std::vector<unsigned> h_off((size_t)nboxes + 1);
+  GV_CUDA(cudaMemcpy2DAsync(h_off.data(), sizeof(unsigned), d_hist, (size_t)nb * sizeof(unsigned),
+                            sizeof(unsigned), (size_t)nboxes, cudaMemcpyDeviceToHost, ctx->stream));
+  GV_CUDA(cudaMemcpyAsync(&h_off[nboxes], d_hist + hn, sizeof(unsigned), cudaMemcpyDeviceToHost,
+                          ctx->stream));
+  GV_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::vector<unsigned long long> off64(h_off.begin(), h_off.end());
+  std::vector<int2> tab;
+  for (int b = 0; b < nboxes; ++b)
+    for (unsigned q = 0; q < h_off[b + 1] - h_off[b]; q += kThreads) tab.push_back(make_int2(b, (int)q));
+  unsigned long long *d_off;
+  int2 *d_tab;
+  uint8_t *d_keep;
+  LShapeDev *d_out;
+  GV_TRY(reserve_t(ctx, S_N2_OFF, (size_t)nboxes + 1, &d_off));
+  GV_TRY(reserve_t(ctx, S_N2_TAB, tab.size() + 1, &d_tab));
+  GV_TRY(reserve_t(ctx, S_N2_KEEP, (size_t)h_off[nboxes] + 1, &d_keep));
+  GV_TRY(reserve_t(ctx, S_N2_OUT, (size_t)nboxes, &d_out));
+  GV_CUDA(cudaMemcpyAsync(d_off, off64.data(), off64.size() * sizeof(unsigned long long),
+                          cudaMemcpyHostToDevice, ctx->stream));
+  if (!tab.empty()) {
+    GV_CUDA(cudaMemcpyAsync(d_tab, tab.data(), tab.size() * sizeof(int2), cudaMemcpyHostToDevice,
+                            ctx->stream));
+    // ref: :150-154 setRadiusSearch(0.4), setMinNeighborsInRadius(10); FLANN gets (float)(r*r)
+    k_n2_neighbors<<<(unsigned)tab.size(), kThreads, 0, ctx->stream>>>(d_x, d_y, d_z, d_idx, d_tab, d_off,
+                                                                      (float)(0.4 * 0.4), 10, d_keep);
+    GV_LAUNCH_CHECK();
+  }
+  k_n2_box<<<nboxes, kThreads, 0, ctx->stream>>>(d_x, d_y, d_z, d_idx, d_off, d_keep, d_out);
+  GV_LAUNCH_CHECK();
+  GV_CUDA(cudaMemcpyAsync(out, d_out, (size_t)nboxes * sizeof(LShapeDev), cudaMemcpyDeviceToHost,
+                          ctx->stream));
   GV_CUDA(cudaStreamSynchronize(ctx->stream));
   return GV_OK;
 }

@@ -1314,6 +1314,377 @@ __global__ void __launch_bounds__(kThreads) k_to_occupancy(const float *__restri
   data[nc - i - 1] = (int8_t)value;
 }
 
+// ----------------------------------------------------------------------------------
+// N1: ground-plane removal (ref: src/cloud_detections.cpp:105-138; oracle gvo_segment_ground).
+// Deterministic batched RANSAC: all hypotheses are scored in ONE pass over the cloud (planes in
+// shared memory, per-warp ballots), the best one is refined by a least-squares fit of its
+// inliers (double moments + cyclic Jacobi, one thread) and the points within the threshold of
+// the refined plane are dropped by an order-preserving compaction.
+// ----------------------------------------------------------------------------------
+constexpr int kMaxHyp = 1024;
+
+__device__ __forceinline__ double block_sum(double v, double *s_red)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int w = 0; w < kThreads / 32; ++w) t += s_red[w];
+  return t;
+}
+
+
+__host__ __device__ __forceinline__ unsigned mix32(unsigned seed, unsigned k)
+{
+  unsigned v = seed ^ (k * 0x9E3779B9u);
+  v ^= v >> 16; v *= 0x85EBCA6Bu;
+  v ^= v >> 13; v *= 0xC2B2AE35u;
+  v ^= v >> 16;
+  return v;
+}
+
+__device__ __forceinline__ float plane_dist(const float4 p, float x, float y, float z)
+{
+  return fabsf(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(p.x, x), __fmul_rn(p.y, y)), __fmul_rn(p.z, z)), p.w));
+}
+
+struct GroundState {
+  float4 plane;        // refined plane (a, b, c, d)
+  float4 best_plane;   // winning hypothesis
+  int best_h, best_score, found, pad;
+  double mom[10];      // count, sum x y z, then xx xy xz yy yz zz about the centroid
+};
+
+__global__ void k_n1_hypotheses(const float *__restrict__ x, const float *__restrict__ y,
+                                const float *__restrict__ z, unsigned n, unsigned seed, int n_hyp,
+                                float4 *__restrict__ planes, int *__restrict__ valid)
+{
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= n_hyp) return;
+  const unsigned i0 = mix32(seed, 3u * h) % n, i1 = mix32(seed, 3u * h + 1u) % n, i2 = mix32(seed, 3u * h + 2u) % n;
+  float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+  int ok = finite3(x[i0], y[i0], z[i0]) && finite3(x[i1], y[i1], z[i1]) && finite3(x[i2], y[i2], z[i2]);
+  if (ok) {
+    const float ux = __fsub_rn(x[i1], x[i0]), uy = __fsub_rn(y[i1], y[i0]), uz = __fsub_rn(z[i1], z[i0]);
+    const float vx = __fsub_rn(x[i2], x[i0]), vy = __fsub_rn(y[i2], y[i0]), vz = __fsub_rn(z[i2], z[i0]);
+    const float cx = __fsub_rn(__fmul_rn(uy, vz), __fmul_rn(uz, vy));
+    const float cy = __fsub_rn(__fmul_rn(uz, vx), __fmul_rn(ux, vz));
+    const float cz = __fsub_rn(__fmul_rn(ux, vy), __fmul_rn(uy, vx));
+    const float n2 = __fadd_rn(__fadd_rn(__fmul_rn(cx, cx), __fmul_rn(cy, cy)), __fmul_rn(cz, cz));
+    ok = n2 > 0.0f && finitef(n2);
+    if (ok) {
+      const float inv = __fdiv_rn(1.0f, __fsqrt_rn(n2));
+      p.x = __fmul_rn(cx, inv); p.y = __fmul_rn(cy, inv); p.z = __fmul_rn(cz, inv);
+      p.w = -__fadd_rn(__fadd_rn(__fmul_rn(p.x, x[i0]), __fmul_rn(p.y, y[i0])), __fmul_rn(p.z, z[i0]));
+    }
+  }
+  planes[h] = p;
+  valid[h] = ok;
+}
+
+__global__ void __launch_bounds__(kThreads) k_n1_score(const float *__restrict__ x, const float *__restrict__ y,
+                                                       const float *__restrict__ z, unsigned long long n,
+                                                       const float4 *__restrict__ planes,
+                                                       const int *__restrict__ valid, int n_hyp,
+                                                       float threshold, int *__restrict__ scores)
+{
+  __shared__ float4 s_p[kMaxHyp];
+  __shared__ int s_cnt[kMaxHyp];
+  for (int h = threadIdx.x; h < n_hyp; h += kThreads) {
+    s_p[h] = valid[h] ? planes[h] : make_float4(0.f, 0.f, 0.f, __int_as_float(0x7fc00000));  // NaN: never an inlier
+    s_cnt[h] = 0;
+  }
+  __syncthreads();
+  const unsigned long long stride = (unsigned long long)gridDim.x * kThreads;
+  const unsigned long long nround = (n + 31ull) & ~31ull;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * kThreads + threadIdx.x; i < nround; i += stride) {
+    const bool live = i < n;
+    const float px = live ? x[i] : 0.f, py = live ? y[i] : 0.f, pz = live ? z[i] : 0.f;
+    for (int h = 0; h < n_hyp; ++h) {
+      const unsigned m = __ballot_sync(0xffffffffu, live && plane_dist(s_p[h], px, py, pz) < threshold);
+      if ((threadIdx.x & 31) == 0 && m) atomicAdd(&s_cnt[h], __popc(m));
+    }
+  }
+  __syncthreads();
+  for (int h = threadIdx.x; h < n_hyp; h += kThreads)
+    if (s_cnt[h]) atomicAdd(&scores[h], s_cnt[h]);
+}
+
+__global__ void k_n1_best(const float4 *__restrict__ planes, const int *__restrict__ scores, int n_hyp,
+                          GroundState *__restrict__ st)
+{
+  // single warp: highest score, lowest hypothesis index on ties
+  int best = 0, bh = -1;
+  for (int h = threadIdx.x; h < n_hyp; h += 32)
+    if (scores[h] > best) { best = scores[h]; bh = h; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const int ob = __shfl_xor_sync(0xffffffffu, best, o), oh = __shfl_xor_sync(0xffffffffu, bh, o);
+    if (ob > best || (ob == best && oh >= 0 && (bh < 0 || oh < bh))) { best = ob; bh = oh; }
+  }
+  if (threadIdx.x == 0) {
+    st->best_h = bh;
+    st->best_score = best;
+    st->found = best >= 3;
+    st->best_plane = bh >= 0 ? planes[bh] : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < 10; ++i) st->mom[i] = 0.0;
+  }
+}
+
+// pass = 0: count + sums of the winning plane's inliers; pass = 1: second moments about the centroid
+__global__ void __launch_bounds__(kThreads) k_n1_moments(const float *__restrict__ x, const float *__restrict__ y,
+                                                         const float *__restrict__ z, unsigned long long n,
+                                                         float threshold, int pass, GroundState *__restrict__ st)
+{
+  __shared__ double s_red[kThreads / 32];
+  if (!st->found) return;
+  const float4 bp = st->best_plane;
+  double a[6] = {0, 0, 0, 0, 0, 0};
+  const double cnt = st->mom[0];
+  const double cx = pass ? st->mom[1] / cnt : 0.0, cy = pass ? st->mom[2] / cnt : 0.0, cz = pass ? st->mom[3] / cnt : 0.0;
+  const unsigned long long stride = (unsigned long long)gridDim.x * kThreads;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+    const float px = x[i], py = y[i], pz = z[i];
+    if (plane_dist(bp, px, py, pz) < threshold) {
+      if (!pass) { a[0] += 1.0; a[1] += px; a[2] += py; a[3] += pz; }
+      else {
+        const double dx = px - cx, dy = py - cy, dz = pz - cz;
+        a[0] += dx * dx; a[1] += dx * dy; a[2] += dx * dz; a[3] += dy * dy; a[4] += dy * dz; a[5] += dz * dz;
+      }
+    }
+  }
+  const int nv = pass ? 6 : 4, base = pass ? 4 : 0;
+  for (int k = 0; k < nv; ++k) {
+    const double t = block_sum(a[k], s_red);
+    if (threadIdx.x == 0 && t != 0.0) atomicAdd(&st->mom[base + k], t);
+  }
+}
+
+__global__ void k_n1_refine(GroundState *__restrict__ st)
+{
+  if (!st->found) return;
+  if (st->best_score <= 3) {  // PCL refines only with more inliers than the sample size
+    st->plane = st->best_plane;
+    return;
+  }
+  // eigenvector of the smallest eigenvalue (cyclic Jacobi, double) — oracle gvo_smallest_eigvec3
+  const double *A = st->mom + 4;
+  double a[3][3] = {{A[0], A[1], A[2]}, {A[1], A[3], A[4]}, {A[2], A[4], A[5]}};
+  double V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  for (int sweep = 0; sweep < 32; ++sweep) {
+    const double off = fabs(a[0][1]) + fabs(a[0][2]) + fabs(a[1][2]);
+    if (off < 1e-300) break;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        if (fabs(a[p][q]) < 1e-300) continue;
+        const double theta = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < 3; ++k) { const double akp = a[k][p], akq = a[k][q]; a[k][p] = c * akp - s * akq; a[k][q] = s * akp + c * akq; }
+        for (int k = 0; k < 3; ++k) { const double apk = a[p][k], aqk = a[q][k]; a[p][k] = c * apk - s * aqk; a[q][k] = s * apk + c * aqk; }
+        for (int k = 0; k < 3; ++k) { const double vkp = V[k][p], vkq = V[k][q]; V[k][p] = c * vkp - s * vkq; V[k][q] = s * vkp + c * vkq; }
+      }
+  }
+  int m = 0;
+  if (a[1][1] < a[m][m]) m = 1;
+  if (a[2][2] < a[m][m]) m = 2;
+  double v[3] = {V[0][m], V[1][m], V[2][m]};
+  const float4 bp = st->best_plane;
+  if (v[0] * bp.x + v[1] * bp.y + v[2] * bp.z < 0) { v[0] = -v[0]; v[1] = -v[1]; v[2] = -v[2]; }
+  const double cnt = st->mom[0], cx = st->mom[1] / cnt, cy = st->mom[2] / cnt, cz = st->mom[3] / cnt;
+  st->plane = make_float4((float)v[0], (float)v[1], (float)v[2], (float)(-(v[0] * cx + v[1] * cy + v[2] * cz)));
+}
+
+// order-preserving removal of the refined plane's inliers: count pass / scatter pass
+__global__ void __launch_bounds__(kThreads) k_n1_count(const float *__restrict__ x, const float *__restrict__ y,
+                                                       const float *__restrict__ z, unsigned long long n,
+                                                       float threshold, const GroundState *__restrict__ st,
+                                                       unsigned *__restrict__ cta_count, uint8_t *__restrict__ keep)
+{
+  const unsigned long long i = (unsigned long long)blockIdx.x * kThreads + threadIdx.x;
+  bool k = false;
+  if (i < n) {
+    k = st->found ? !(plane_dist(st->plane, x[i], y[i], z[i]) < threshold) : true;
+    if (keep) keep[i] = k;
+  }
+  const int c = __syncthreads_count(k);
+  if (threadIdx.x == 0) cta_count[blockIdx.x] = (unsigned)c;
+}
+
+__global__ void __launch_bounds__(kThreads) k_n1_scatter(const float *__restrict__ x, const float *__restrict__ y,
+                                                         const float *__restrict__ z, unsigned long long n,
+                                                         float threshold, const GroundState *__restrict__ st,
+                                                         const unsigned *__restrict__ cta_base,
+                                                         float *__restrict__ ox, float *__restrict__ oy,
+                                                         float *__restrict__ oz)
+{
+  __shared__ unsigned s_warp[kThreads / 32];
+  const unsigned long long i = (unsigned long long)blockIdx.x * kThreads + threadIdx.x;
+  const bool k = i < n && (st->found ? !(plane_dist(st->plane, x[i], y[i], z[i]) < threshold) : true);
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned m = __ballot_sync(0xffffffffu, k);
+  if (lane == 0) s_warp[warp] = __popc(m);
+  __syncthreads();
+  unsigned base = cta_base[blockIdx.x];
+  for (unsigned w = 0; w < warp; ++w) base += s_warp[w];
+  if (k) {
+    const unsigned long long o = (unsigned long long)base + __popc(m & ((1u << lane) - 1u));
+    ox[o] = x[i]; oy[o] = y[i]; oz[o] = z[i];
+  }
+}
+
+// ----------------------------------------------------------------------------------
+// N2: per-box radius-outlier filter + PCA box (ref: src/cloud_detections.cpp:140-247;
+// oracle gvo_radius_outlier_keep / gvo_bbox_pose).  Points arrive partitioned by box
+// (k_label_hist/scatter): box b owns positions [off[b], off[b+1]) of the index list.
+// ----------------------------------------------------------------------------------
+struct LShapeDev {  // binary twin of gv_lshape / oracle gvo_lshape
+  int kept;
+  float centroid_y, mean_z, mean_x, major_z, major_x, minor_z, minor_x, length, width, angle_deg;
+  double qx, qy, qz, qw;
+};
+
+// ref: :150-154 RadiusOutlierRemoval(0.4, 10): keep iff #{j : |p_j - p_i|^2 < r2} (self included)
+// > min_nb.  One CTA = 256 query points of one box; the box's points stream through shared
+// memory.  d2 is evaluated exactly like the oracle: (dx*dx + dy*dy) + dz*dz, single roundings.
+__global__ void __launch_bounds__(kThreads) k_n2_neighbors(
+  const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ z,
+  const unsigned *__restrict__ indices, const int2 *__restrict__ block_tab /* (box, first query) */,
+  const unsigned long long *__restrict__ offsets, float r2, int min_nb, uint8_t *__restrict__ keep)
+{
+  __shared__ float sx[kThreads], sy[kThreads], sz[kThreads];
+  const int2 bt = block_tab[blockIdx.x];
+  const unsigned long long b0 = offsets[bt.x], b1 = offsets[bt.x + 1];
+  const unsigned long long q = b0 + (unsigned)bt.y + threadIdx.x;
+  const bool live = q < b1;
+  float qx = 0.f, qy = 0.f, qz = 0.f;
+  if (live) {
+    const unsigned i = indices[q];
+    qx = x[i]; qy = y[i]; qz = z[i];
+  }
+  int k = 0;
+  for (unsigned long long t = b0; t < b1; t += kThreads) {
+    const unsigned long long j = t + threadIdx.x;
+    __syncthreads();
+    if (j < b1) {
+      const unsigned i = indices[j];
+      sx[threadIdx.x] = x[i]; sy[threadIdx.x] = y[i]; sz[threadIdx.x] = z[i];
+    }
+    __syncthreads();
+    const int m = (int)(b1 - t < (unsigned long long)kThreads ? b1 - t : (unsigned long long)kThreads);
+    if (live)
+      for (int c = 0; c < m; ++c) {
+        const float dx = __fsub_rn(sx[c], qx), dy = __fsub_rn(sy[c], qy), dz = __fsub_rn(sz[c], qz);
+        const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        k += d2 < r2 ? 1 : 0;
+      }
+  }
+  if (live) keep[q] = k > min_nb ? 1 : 0;
+}
+
+// ref: :157-158 centroid, :189-191 cv::PCA on rows (z, x), :204-237 extents, :232-247 pose.
+// One CTA per box.  Moments are reduced in double (the reference accumulates in float in
+// input order: results agree to float rounding, compared with a tolerance in the tests); the
+// extents use the oracle's float expression on the float mean/axes.
+__global__ void __launch_bounds__(kThreads) k_n2_box(
+  const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ z,
+  const unsigned *__restrict__ indices, const unsigned long long *__restrict__ offsets,
+  const uint8_t *__restrict__ keep, LShapeDev *__restrict__ out)
+{
+  __shared__ double s_red[kThreads / 32];
+  __shared__ float s_ax[6];  // mean_z, mean_x, major_z, major_x, minor_z, minor_x
+  __shared__ float s_mm[4][kThreads / 32];
+  const int b = blockIdx.x;
+  const unsigned long long b0 = offsets[b], b1 = offsets[b + 1];
+  double cnt = 0, sy = 0, sz = 0, sx = 0;
+  for (unsigned long long j = b0 + threadIdx.x; j < b1; j += kThreads)
+    if (keep[j]) {
+      const unsigned i = indices[j];
+      cnt += 1.0; sy += (double)y[i]; sz += (double)z[i]; sx += (double)x[i];
+    }
+  cnt = block_sum(cnt, s_red);
+  sy = block_sum(sy, s_red);
+  sz = block_sum(sz, s_red);
+  sx = block_sum(sx, s_red);
+  LShapeDev r;
+  memset(&r, 0, sizeof(r));
+  r.qw = 1.0;
+  r.kept = (int)cnt;
+  if (r.kept == 0) {  // ref: :201-202 data.empty() -> box skipped
+    if (threadIdx.x == 0) out[b] = r;
+    return;
+  }
+  const double mz = sz / cnt, mx = sx / cnt;
+  double czz = 0, czx = 0, cxx = 0;
+  for (unsigned long long j = b0 + threadIdx.x; j < b1; j += kThreads)
+    if (keep[j]) {
+      const unsigned i = indices[j];
+      const double dz = (double)z[i] - mz, dx = (double)x[i] - mx;
+      czz += dz * dz; czx += dz * dx; cxx += dx * dx;
+    }
+  czz = block_sum(czz, s_red) / cnt;
+  czx = block_sum(czx, s_red) / cnt;
+  cxx = block_sum(cxx, s_red) / cnt;
+  if (threadIdx.x == 0) {
+    // symmetric 2x2 eigen decomposition, larger eigenvalue first (oracle gvo_bbox_pose)
+    const double tr = czz + cxx, df = czz - cxx;
+    const double rad = sqrt(df * df + 4.0 * czx * czx);
+    const double l1 = 0.5 * (tr + rad);
+    double vz, vx;
+    if (fabs(czx) > 1e-300) { vz = l1 - cxx; vx = czx; }
+    else if (czz >= cxx) { vz = 1.0; vx = 0.0; }
+    else { vz = 0.0; vx = 1.0; }
+    const double nv = sqrt(vz * vz + vx * vx);
+    vz /= nv; vx /= nv;
+    if (vz < 0 || (vz == 0 && vx < 0)) { vz = -vz; vx = -vx; }
+    s_ax[0] = (float)mz; s_ax[1] = (float)mx;
+    s_ax[2] = (float)vz; s_ax[3] = (float)vx;
+    s_ax[4] = (float)(-vx); s_ax[5] = (float)vz;
+  }
+  __syncthreads();
+  const float fmz = s_ax[0], fmx = s_ax[1], az = s_ax[2], ax = s_ax[3], wz = s_ax[4], wx = s_ax[5];
+  float minL = 3.402823466e+38f, maxL = -3.402823466e+38f, minW = minL, maxW = maxL;
+  for (unsigned long long j = b0 + threadIdx.x; j < b1; j += kThreads)
+    if (keep[j]) {
+      const unsigned i = indices[j];
+      const float dz = __fsub_rn(z[i], fmz), dx = __fsub_rn(x[i], fmx);
+      const float pL = __fadd_rn(__fmul_rn(dz, az), __fmul_rn(dx, ax));
+      const float pW = __fadd_rn(__fmul_rn(dz, wz), __fmul_rn(dx, wx));
+      minL = fminf(minL, pL); maxL = fmaxf(maxL, pL);
+      minW = fminf(minW, pW); maxW = fmaxf(maxW, pW);
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    minL = fminf(minL, __shfl_xor_sync(0xffffffffu, minL, o));
+    maxL = fmaxf(maxL, __shfl_xor_sync(0xffffffffu, maxL, o));
+    minW = fminf(minW, __shfl_xor_sync(0xffffffffu, minW, o));
+    maxW = fmaxf(maxW, __shfl_xor_sync(0xffffffffu, maxW, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_mm[0][threadIdx.x >> 5] = minL; s_mm[1][threadIdx.x >> 5] = maxL;
+    s_mm[2][threadIdx.x >> 5] = minW; s_mm[3][threadIdx.x >> 5] = maxW;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kThreads / 32; ++w) {
+      s_mm[0][0] = fminf(s_mm[0][0], s_mm[0][w]); s_mm[1][0] = fmaxf(s_mm[1][0], s_mm[1][w]);
+      s_mm[2][0] = fminf(s_mm[2][0], s_mm[2][w]); s_mm[3][0] = fmaxf(s_mm[3][0], s_mm[3][w]);
+    }
+    r.centroid_y = (float)(sy / cnt);
+    r.mean_z = fmz; r.mean_x = fmx;
+    r.major_z = az; r.major_x = ax; r.minor_z = wz; r.minor_x = wx;
+    r.length = __fsub_rn(s_mm[1][0], s_mm[0][0]);
+    r.width = __fsub_rn(s_mm[3][0], s_mm[2][0]);
+    // ref: :232 degrees; :246-247 setRPY(0, -angle, 0) takes the DEGREE value as radians (kept)
+    r.angle_deg = __fdiv_rn(__fmul_rn(atan2f(ax, az), 180.0f), 3.14159265358979323846f);
+    const double hp = -(double)r.angle_deg * 0.5;
+    r.qx = 0.0; r.qy = sin(hp); r.qz = 0.0; r.qw = cos(hp);
+    out[b] = r;
+  }
+}
+
 // ref: src/cloud_detections.cpp:282-283 compares float u,v (promoted) against the double box
 // bounds, inclusive.  u >= x_min  <=>  u >= RU_f32(x_min)  and  u <= x_max  <=>  u <= RD_f32(x_max)
 // for every float u, so rounding the bounds once (toward +inf for mins, -inf for maxes) turns

@@ -155,6 +155,38 @@ GV_API int gv_project_kdtree(gv_ctx *ctx, int cam, const float *x, const float *
 GV_API int gv_partition_by_label(gv_ctx *ctx, const int16_t *labels, size_t n, int nboxes,
                                  uint32_t *indices_out, uint64_t *offsets_out);
 
+/* "Next" row N1: the step that precedes extractCloudPerBBox inside computeBBoxPose —
+ * cloud_detections::segmentGroundPlane (ref: src/cloud_detections.cpp:105-138; decl
+ * cloud_detections.hpp:40-41): RANSAC plane (distance threshold 0.04 m, coefficients refined by
+ * least squares) and removal of its inliers, order preserved.  PCL's random sample stream cannot
+ * be reproduced, so the hypotheses are a deterministic counter-hashed set (seed, n_hyp <= 1024)
+ * scored in one pass; parity is against the repository's oracle, which fixes the same set.
+ * Outputs: compacted cloud (ox,oy,oz need room for n floats), *m_out points kept, plane_out
+ * (a,b,c,d).  *found_out = 0 when no model exists: the reference then returns an EMPTY cloud
+ * (:122-126) and computeBBoxPose returns {} (:308-309); *m_out is 0 in that case. */
+GV_API int gv_segment_ground(gv_ctx *ctx, const float *x, const float *y, const float *z, size_t n,
+                             float threshold, uint32_t seed, int n_hyp, float *ox, float *oy,
+                             float *oz, size_t *m_out, float *plane_out, int *found_out);
+
+/* "Next" row N2: the step that follows extractCloudPerBBox inside computeBBoxPose —
+ * cloud_detections::bboxPoseEstimation + computePCABoundingBox
+ * (ref: src/cloud_detections.cpp:140-247; decls cloud_detections.hpp:43-44,54).
+ * Per box: pcl::RadiusOutlierRemoval(0.4 m, 10 neighbours), centroid, cv::PCA on (z, x), extents
+ * along the principal axes.  Input: the camera-frame cloud + the labels gv_fuse produced.
+ * out[b].kept == 0 means the reference would emit no pose for box b (:201-202).  The eigenvector
+ * sign is normalised (major_z >= 0); OpenCV's is arbitrary. */
+typedef struct {
+  int32_t kept;                /* points that survived the radius-outlier filter           */
+  float centroid_y;            /* pose.position.y (:209)                                   */
+  float mean_z, mean_x;        /* PCA mean: pose.position.z, pose.position.x (:235-237)     */
+  float major_z, major_x, minor_z, minor_x; /* PCA eigenvectors, rows (z, x)               */
+  float length, width;         /* extents along major / minor (:224-225)                   */
+  float angle_deg;             /* atan2(major.y, major.x) * 180 / pi (:232)                */
+  double qx, qy, qz, qw;       /* tf2::Quaternion::setRPY(0, -angle_deg, 0) (:246-247)     */
+} gv_lshape;
+GV_API int gv_bbox_pose(gv_ctx *ctx, const float *x, const float *y, const float *z, size_t n,
+                        const int16_t *labels, int nboxes, gv_lshape *out);
+
 /* --------------------------------------------------------- grid state (R6) --- */
 /* ref: OccupancyGridMap::OccupancyGridMap, src/occupancy_grid.cpp:4-14
  * (decl include/grid_vision/occupancy_grid.hpp:16): size = round(length/res), centre

@@ -609,6 +609,145 @@ void gvo_finalize(gvo_grid *g, int32_t k_decay, const double *corners, int nfoot
 }
 
 /* ------------------------------------------------------------------------- */
+/* N1  ground-plane removal (src/cloud_detections.cpp:105-138)                */
+/* ------------------------------------------------------------------------- */
+
+static inline uint32_t gvo_mix32(uint32_t seed, uint32_t k)
+{
+  /* counter-based integer hash (two rounds of a multiply-xorshift mixer), identical on the GPU */
+  uint32_t v = seed ^ (k * 0x9E3779B9u);
+  v ^= v >> 16; v *= 0x85EBCA6Bu;
+  v ^= v >> 13; v *= 0xC2B2AE35u;
+  v ^= v >> 16;
+  return v;
+}
+
+static inline float gvo_plane_dist(const float p[4], float x, float y, float z)
+{
+  const float a = p[0] * x, b = p[1] * y, c = p[2] * z;
+  const float s1 = a + b;
+  const float s2 = s1 + c;
+  return fabsf(s2 + p[3]);
+}
+
+/* plane through three points, float; returns 0 for a degenerate / non-finite sample */
+static int gvo_plane_from3(const float *x, const float *y, const float *z, size_t i0, size_t i1,
+                           size_t i2, float p[4])
+{
+  if (!gvo_finite3(x[i0], y[i0], z[i0]) || !gvo_finite3(x[i1], y[i1], z[i1]) ||
+      !gvo_finite3(x[i2], y[i2], z[i2]))
+    return 0;
+  const float ux = x[i1] - x[i0], uy = y[i1] - y[i0], uz = z[i1] - z[i0];
+  const float vx = x[i2] - x[i0], vy = y[i2] - y[i0], vz = z[i2] - z[i0];
+  const float cx = uy * vz - uz * vy, cy = uz * vx - ux * vz, cz = ux * vy - uy * vx;
+  const float n2 = (cx * cx + cy * cy) + cz * cz;
+  if (!(n2 > 0.0f) || !isfinite(n2)) return 0;
+  const float inv = 1.0f / sqrtf(n2);
+  p[0] = cx * inv; p[1] = cy * inv; p[2] = cz * inv;
+  p[3] = -((p[0] * x[i0] + p[1] * y[i0]) + p[2] * z[i0]);
+  return 1;
+}
+
+/* eigenvector of the smallest eigenvalue of a symmetric 3x3 matrix (cyclic Jacobi, double) */
+static void gvo_smallest_eigvec3(const double A[6] /* xx xy xz yy yz zz */, double v[3])
+{
+  double a[3][3] = {{A[0], A[1], A[2]}, {A[1], A[3], A[4]}, {A[2], A[4], A[5]}};
+  double V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  for (int sweep = 0; sweep < 32; ++sweep) {
+    const double off = fabs(a[0][1]) + fabs(a[0][2]) + fabs(a[1][2]);
+    if (off < 1e-300) break;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        if (fabs(a[p][q]) < 1e-300) continue;
+        const double theta = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < 3; ++k) {
+          const double akp = a[k][p], akq = a[k][q];
+          a[k][p] = c * akp - s * akq;
+          a[k][q] = s * akp + c * akq;
+        }
+        for (int k = 0; k < 3; ++k) {
+          const double apk = a[p][k], aqk = a[q][k];
+          a[p][k] = c * apk - s * aqk;
+          a[q][k] = s * apk + c * aqk;
+        }
+        for (int k = 0; k < 3; ++k) {
+          const double vkp = V[k][p], vkq = V[k][q];
+          V[k][p] = c * vkp - s * vkq;
+          V[k][q] = s * vkp + c * vkq;
+        }
+      }
+  }
+  int m = 0;
+  if (a[1][1] < a[m][m]) m = 1;
+  if (a[2][2] < a[m][m]) m = 2;
+  v[0] = V[0][m]; v[1] = V[1][m]; v[2] = V[2][m];
+}
+
+int64_t gvo_segment_ground(const float *x, const float *y, const float *z, size_t n, float threshold,
+                           uint32_t seed, int32_t n_hyp, uint8_t *keep, float plane[4],
+                           int32_t *best_h, int32_t *best_score)
+{
+  for (size_t i = 0; i < n; ++i) keep[i] = 1;
+  *best_h = -1;
+  *best_score = 0;
+  plane[0] = plane[1] = plane[2] = plane[3] = 0.0f;
+  if (n < 3) return -1;
+  float bp[4] = {0, 0, 0, 0};
+  for (int32_t h = 0; h < n_hyp; ++h) {
+    float p[4];
+    const size_t i0 = gvo_mix32(seed, 3u * (uint32_t)h) % n, i1 = gvo_mix32(seed, 3u * (uint32_t)h + 1u) % n,
+                 i2 = gvo_mix32(seed, 3u * (uint32_t)h + 2u) % n;
+    if (!gvo_plane_from3(x, y, z, i0, i1, i2, p)) continue;
+    int32_t score = 0;
+    for (size_t i = 0; i < n; ++i) score += gvo_plane_dist(p, x[i], y[i], z[i]) < threshold;
+    if (score > *best_score) {
+      *best_score = score;
+      *best_h = h;
+      memcpy(bp, p, sizeof(bp));
+    }
+  }
+  if (*best_score < 3) return -1; /* :122-126 no planar model -> the reference returns an empty cloud */
+  if (*best_score == 3) {         /* PCL refines only with more inliers than the sample size */
+    memcpy(plane, bp, sizeof(bp));
+    int64_t kept3 = 0;
+    for (size_t i = 0; i < n; ++i) {
+      keep[i] = !(gvo_plane_dist(plane, x[i], y[i], z[i]) < threshold);
+      kept3 += keep[i];
+    }
+    return kept3;
+  }
+  /* setOptimizeCoefficients(true): least-squares plane of the inliers */
+  double c[3] = {0, 0, 0}, m = 0;
+  for (size_t i = 0; i < n; ++i)
+    if (gvo_plane_dist(bp, x[i], y[i], z[i]) < threshold) {
+      c[0] += x[i]; c[1] += y[i]; c[2] += z[i];
+      m += 1;
+    }
+  c[0] /= m; c[1] /= m; c[2] /= m;
+  double A[6] = {0, 0, 0, 0, 0, 0};
+  for (size_t i = 0; i < n; ++i)
+    if (gvo_plane_dist(bp, x[i], y[i], z[i]) < threshold) {
+      const double dx = x[i] - c[0], dy = y[i] - c[1], dz = z[i] - c[2];
+      A[0] += dx * dx; A[1] += dx * dy; A[2] += dx * dz;
+      A[3] += dy * dy; A[4] += dy * dz; A[5] += dz * dz;
+    }
+  double v[3];
+  gvo_smallest_eigvec3(A, v);
+  /* orient like the RANSAC hypothesis so the refinement never flips the normal */
+  if (v[0] * bp[0] + v[1] * bp[1] + v[2] * bp[2] < 0) { v[0] = -v[0]; v[1] = -v[1]; v[2] = -v[2]; }
+  plane[0] = (float)v[0]; plane[1] = (float)v[1]; plane[2] = (float)v[2];
+  plane[3] = (float)(-(v[0] * c[0] + v[1] * c[1] + v[2] * c[2]));
+  int64_t kept = 0;
+  for (size_t i = 0; i < n; ++i) {
+    keep[i] = !(gvo_plane_dist(plane, x[i], y[i], z[i]) < threshold); /* :128-135 setNegative(true) */
+    kept += keep[i];
+  }
+  return kept;
+}
+
+/* ------------------------------------------------------------------------- */
 /* N2  radius outlier removal + PCA box (src/cloud_detections.cpp:140-247)    */
 /* ------------------------------------------------------------------------- */
 

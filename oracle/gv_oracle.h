@@ -158,6 +158,26 @@ int32_t gvo_bresenham_cells(int32_t sx, int32_t sy, int32_t ex, int32_t ey, int3
  * hit = miss = 0.  corners: nfoot x 4 x (x,y) doubles (may be NULL when nfoot==0). */
 void gvo_finalize(gvo_grid *g, int32_t k_decay, const double *corners, int nfoot);
 
+/* N1 (next row): cloud_detections::segmentGroundPlane (src/cloud_detections.cpp:105-138):
+ * pcl::SACSegmentation(SACMODEL_PLANE, SAC_RANSAC, distance threshold 0.04, optimise
+ * coefficients) then ExtractIndices(negative) removes the plane's inliers, order kept; no model
+ * -> EMPTY cloud (:122-126).  PCL draws its samples from a boost::mt19937 stream that cannot be
+ * reproduced offline, so parity with PCL is statistical by nature; THIS restatement fixes a
+ * deterministic hypothesis set instead, which the GPU shares bit for bit:
+ *   - hypothesis h in [0, n_hyp): three point indices mix32(seed, 3h+j) % n; invalid if a sample
+ *     is non-finite or the triangle is degenerate; plane = normalised (p1-p0) x (p2-p0), float
+ *   - score = #{ i : |a x + b y + c z + d| < threshold }   (float, left-to-right, strict <)
+ *   - best = highest score, lowest h on ties; no valid hypothesis (score < 3) -> no model;
+ *     exactly 3 inliers -> the hypothesis itself is the plane (PCL refines only beyond the sample size)
+ *   - refinement (optimizeModelCoefficients): centroid + covariance of the best plane's inliers
+ *     in double, normal = eigenvector of the smallest eigenvalue (cyclic Jacobi), d = -n.c
+ *   - removed = points within threshold of the refined plane (selectWithinDistance)
+ * keep[i] = 1 for points that stay.  Returns the number kept, or -1 when no model was found
+ * (the reference then returns an empty cloud). */
+int64_t gvo_segment_ground(const float *x, const float *y, const float *z, size_t n, float threshold,
+                           uint32_t seed, int32_t n_hyp, uint8_t *keep, float plane[4],
+                           int32_t *best_h, int32_t *best_score);
+
 /* N2 (next row): cloud_detections::bboxPoseEstimation + computePCABoundingBox
  * (src/cloud_detections.cpp:140-247) for ONE per-box cloud in the camera frame.
  *   1. pcl::RadiusOutlierRemoval(r = 0.4, min neighbours 10): keep point i iff the number of

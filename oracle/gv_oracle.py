@@ -175,6 +175,20 @@ def bresenham_cells(sx, sy, ex, ey):
     return out
 
 
+def segment_ground(x, y, z, threshold=0.04, seed=12345, n_hyp=256):
+    """N1 -> (keep mask or None when no model, plane[4], best hypothesis, best score)."""
+    x, y, z = _f32(x), _f32(y), _f32(z)
+    keep = np.ones(x.size, np.uint8)
+    plane = np.zeros(4, np.float32)
+    bh, bs = C.c_int32(-1), C.c_int32(0)
+    lib().gvo_segment_ground.restype = C.c_int64
+    kept = lib().gvo_segment_ground(_p(x, C.c_float), _p(y, C.c_float), _p(z, C.c_float),
+                                    C.c_size_t(x.size), C.c_float(threshold), C.c_uint32(seed),
+                                    C.c_int32(n_hyp), _p(keep, C.c_uint8), _p(plane, C.c_float),
+                                    C.byref(bh), C.byref(bs))
+    return (None if kept < 0 else keep.astype(bool)), plane, bh.value, bs.value
+
+
 def radius_outlier_keep(x, y, z, radius=0.4, min_neighbors=10):
     x, y, z = _f32(x), _f32(y), _f32(z)
     keep = np.zeros(x.size, np.uint8)
