@@ -811,21 +811,18 @@ __global__ void __launch_bounds__(kThreads) k_label_scatter(const int16_t *__res
 // All beams binned since the last flush share one start cell s, and a Bresenham line is a pure
 // function of (start, end), so the traversed-cell multiset of the whole batch is
 //   sum over distinct end cells e of  w_e * line(s, e)           (exact: integer sums commute).
-// Work item = up to 256 end cells that lie side by side at the same major-axis distance D from s
-// (a piece of the column x = sx +- D for x-major lines, |dy| <= D; of the row y = sy +- D for
-// y-major lines, |dx| < D — the grid_map LineIterator's own case split).  One warp walks the
-// 32 lines of an item in lock step:
+// End cells are organised by (direction, major-axis distance D from s): pieces of the column
+// x = sx +- D (x-major lines, |dy| <= D) and of the row y = sy +- D (y-major lines, |dx| < D) —
+// the grid_map LineIterator's own case split.  32 end cells of one such piece, taken in order,
+// give 32 lines that one warp can walk in lock step:
 //   * all 32 lines have exactly D + 1 cells: no divergence, no tail;
 //   * at step k every lane is at the same major coordinate and the minor coordinates are
 //     monotone in the lane index, so equal cells form contiguous lane runs: one shuffle + one
 //     ballot find the runs, and the run's weight is a difference of the warp prefix sum of w_e
-//     (computed once, the weights do not change along the walk): ONE RED per distinct cell;
-//   * lanes without beams carry weight 0 and ride along; an item with no beams is skipped.
-// Items are sorted by decreasing D and handed out through an atomic counter (longest first).
-// The end cells themselves are settled here too (hit += high word, miss += low - high) and the
-// ends plane is cleared.  Multi-GPU: item i belongs to rank i % world (the table is identical
-// on every rank).
-// grid_map LineIterator restatement: oracle gvo_line_init / gvo_line_step.
+//     (computed once, the weights do not change along the walk): ONE RED per distinct cell.
+// The end cells themselves are settled too (hit += high word, miss += low - high) and the ends
+// plane is cleared.  Multi-GPU: span i belongs to rank i % world (the table is identical on
+// every rank).  LineIterator restatement: oracle gvo_line_init / gvo_line_step.
 // ----------------------------------------------------------------------------------
 // Peer-memory views of one plane on every rank (cudaIpc-mapped, NVLink P2P); p[rank] is local.
 constexpr int kMaxPeers = 16;
@@ -840,10 +837,10 @@ struct SweepEntry {
   int m0, m1;  // inclusive range of the minor coordinate (absolute index), clipped to the map
 };
 
-// Scheduling: the item list is sorted by decreasing D; rank r owns items r, r + world, ... and
-// warps pull that rank's items through one atomic counter, longest first.  (Measured: static
-// round-robin is 20 % slower — most items carry no beams and the busy ones cluster — and cutting
-// lines into segments for more parallelism costs more in set-up than it gains.)
+// Scheduling: the span list is sorted by decreasing D; rank r owns spans r, r + world, ... and
+// warps pull work through an atomic counter, longest first.  (Measured: static round-robin is
+// 20 % slower — most spans carry no beams and the busy ones cluster — and cutting lines into
+// segments for more parallelism costs more in set-up than it gains.)
 __device__ __forceinline__ int sweep_find_entry(const unsigned *__restrict__ prefix, int n_entries,
                                                 unsigned unit)
 {
