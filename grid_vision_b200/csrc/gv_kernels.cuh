@@ -872,6 +872,9 @@ __device__ __forceinline__ size_t sweep_end_cell(const SweepEntry &E, int mc, in
 constexpr int kSpanChunks = 32;
 constexpr int kSpanCells = 32 * kSpanChunks;
 
+// One CTA per span: 8 warps x 4 chunks, four independent loads per thread, a block prefix over
+// the per-chunk ballots, one atomic per span to reserve its batches.  (A warp-per-span version
+// spent ~0.1 ms in 64 dependent loads per warp whatever the rank's share of the spans.)
 __global__ void __launch_bounds__(kThreads) k_sweep_compact(
   unsigned long long *__restrict__ ends, int32_t *__restrict__ hit, int32_t *__restrict__ miss,
   const SweepEntry *__restrict__ entries, const unsigned *__restrict__ item_prefix, int n_entries,
@@ -880,67 +883,84 @@ __global__ void __launch_bounds__(kThreads) k_sweep_compact(
   int *__restrict__ batch_entry, int *__restrict__ batch_mi, unsigned *__restrict__ batch_w,
   unsigned long long *__restrict__ stats)
 {
-  const unsigned lane = threadIdx.x & 31;
+  constexpr int kWarps = kThreads / 32;
+  constexpr int kPer = kSpanChunks / kWarps;  // chunks per warp
+  static_assert(kSpanChunks % kWarps == 0, "span must split evenly over the warps");
+  __shared__ unsigned s_item, s_base;
+  __shared__ int s_cnt[kSpanChunks], s_last[kWarps];
+  const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   unsigned long long st_beams = 0, st_logical = 0, st_lines = 0;
   for (;;) {
-    unsigned t = 0;
-    if (lane == 0) t = atomicAdd(counters, 1u);
-    t = __shfl_sync(0xffffffffu, t, 0);
-    const unsigned long long item64 = (unsigned long long)t * world + rank;
+    __syncthreads();  // s_item / s_cnt of the previous span are no longer read
+    if (threadIdx.x == 0) s_item = atomicAdd(counters, 1u);
+    __syncthreads();
+    const unsigned long long item64 = (unsigned long long)s_item * world + rank;
     if (item64 >= n_items) break;
     const unsigned item = (unsigned)item64;
     const int ei = sweep_find_entry(item_prefix, n_entries, item);
     const SweepEntry E = entries[ei];
     const int span0 = E.m0 + (int)(item - item_prefix[ei]) * kSpanCells;
-    // pass 1: how many non-empty cells
-    int count = 0;
-#pragma unroll 1
-    for (int c = 0; c < kSpanChunks && span0 + c * 32 <= E.m1; ++c) {
-      const int mi = span0 + c * 32 + (int)lane;
+    // four independent loads per thread
+    unsigned long long e[kPer];
+    size_t elin[kPer];
+    int mi[kPer];
+    int last = -1;
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      mi[j] = span0 + ((int)wid * kPer + j) * 32 + (int)lane;
       int ex, ey;
-      const size_t elin = sweep_end_cell(E, mi <= E.m1 ? mi : E.m1, sx, sy, nx, ex, ey);
-      const unsigned long long e = mi <= E.m1 ? ends[elin] : 0ull;
-      count += __popc(__ballot_sync(0xffffffffu, e != 0ull));
+      elin[j] = sweep_end_cell(E, mi[j] <= E.m1 ? mi[j] : E.m1, sx, sy, nx, ex, ey);
+      e[j] = mi[j] <= E.m1 ? ends[elin[j]] : 0ull;
     }
-    if (count == 0) continue;
+    unsigned nz[kPer];
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      nz[j] = __ballot_sync(0xffffffffu, e[j] != 0ull);
+      if (lane == 0) s_cnt[wid * kPer + j] = __popc(nz[j]);
+      if (nz[j]) last = span0 + ((int)wid * kPer + j) * 32 + (31 - __clz((int)nz[j]));
+    }
+    if (lane == 0) s_last[wid] = last;
+    __syncthreads();
+    int count = 0, before = 0, last_mi = E.m0;
+    for (int c = 0; c < kSpanChunks; ++c) {
+      if (c == (int)wid * kPer) before = count;
+      count += s_cnt[c];
+    }
+    for (int w = 0; w < kWarps; ++w)
+      if (s_last[w] >= 0) last_mi = s_last[w];  // warps hold ascending cells: the last hit wins
+    if (count == 0) continue;  // block-uniform
     const int nbatch = E.D > 0 ? (count + 31) >> 5 : 0;  // the start cell itself has no line to walk
-    unsigned base = 0;
-    if (lane == 0 && nbatch) base = atomicAdd(counters + 1, (unsigned)nbatch);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    // pass 2: settle + clear the end cells, append them in order
-    int pos = 0, last_mi = E.m0;
-#pragma unroll 1
-    for (int c = 0; c < kSpanChunks && span0 + c * 32 <= E.m1; ++c) {
-      const int mi = span0 + c * 32 + (int)lane;
-      int ex, ey;
-      const size_t elin = sweep_end_cell(E, mi <= E.m1 ? mi : E.m1, sx, sy, nx, ex, ey);
-      const unsigned long long e = mi <= E.m1 ? ends[elin] : 0ull;
-      const unsigned nz = __ballot_sync(0xffffffffu, e != 0ull);
-      if (e != 0ull) {
-        const unsigned w = (unsigned)(e & 0xffffffffull), hits = (unsigned)(e >> 32);
+    if (threadIdx.x == 0 && nbatch) s_base = atomicAdd(counters + 1, (unsigned)nbatch);
+    __syncthreads();
+    const size_t base = nbatch ? (size_t)s_base * 32 : 0;
+    // settle + clear the end cells, append them in order
+    int pos = before;
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      if (e[j] != 0ull) {
+        const unsigned w = (unsigned)(e[j] & 0xffffffffull), hits = (unsigned)(e[j] >> 32);
         if (nbatch) {
-          const size_t o = (size_t)base * 32 + (size_t)(pos + __popc(nz & ((1u << lane) - 1u)));
-          batch_mi[o] = mi;
+          const size_t o = base + (size_t)(pos + __popc(nz[j] & ((1u << lane) - 1u)));
+          batch_mi[o] = mi[j];
           batch_w[o] = w;
         }
-        if (clear_ends) ends[elin] = 0ull;     // single GPU: this lane is the only reader of the cell
-        if (hits) hit[elin] += (int32_t)hits;  // only this lane ever writes hit[elin] in this kernel
-        if (w - hits) atomicAdd(miss + elin, (int32_t)(w - hits));  // other lines pass through it
+        if (clear_ends) ends[elin[j]] = 0ull;     // single GPU: this thread is the only reader of the cell
+        if (hits) hit[elin[j]] += (int32_t)hits;  // only this thread ever writes hit[elin] in this kernel
+        if (w - hits) atomicAdd(miss + elin[j], (int32_t)(w - hits));  // other lines pass through it
         st_beams += w;
         st_logical += (unsigned long long)w * (unsigned)(E.D + 1);
         st_lines += 1;
       }
-      if (nz) last_mi = span0 + c * 32 + (31 - __clz((int)nz));
-      pos += __popc(nz);
+      pos += __popc(nz[j]);
     }
     if (nbatch) {
       // pad the last batch with weight-0 shadows of the last line, tag every batch with its entry
       const int padded = nbatch * 32;
-      for (int i = count + (int)lane; i < padded; i += 32) {
-        batch_mi[(size_t)base * 32 + i] = last_mi;
-        batch_w[(size_t)base * 32 + i] = 0u;
+      for (int i = count + (int)threadIdx.x; i < padded; i += kThreads) {
+        batch_mi[base + i] = last_mi;
+        batch_w[base + i] = 0u;
       }
-      for (int b = (int)lane; b < nbatch; b += 32) batch_entry[base + b] = ei;
+      for (int b = (int)threadIdx.x; b < nbatch; b += kThreads) batch_entry[s_base + b] = ei;
     }
   }
 #pragma unroll
