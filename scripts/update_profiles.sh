@@ -6,7 +6,7 @@ TAG=${1:-r01}
 FR=${2:-4096}
 export FR
 python scripts/summarize_ncu.py gpurun_out/prof.ncu-rep gpurun_out/launches.csv profiles/${TAG}_ncu_c3_${FR}frames.md \
-  "Round 1 — ncu, bench.py --frames ${FR} --steps 2 --warmup 1 --no-e2e --no-cpu --no-extra (C3, $((FR*131072)) points/launch), 1x B200"
+  "Round 1 — ncu, bench.py --frames ${FR} --steps 1 --warmup 1 --no-e2e --no-cpu --no-extra (C3, $((FR*131072)) points/launch), 1x B200"
 cp gpurun_out/launches.csv profiles/${TAG}_launches_c3_${FR}frames.csv
 python - <<'PY'
 import csv, io, json, subprocess
