@@ -256,7 +256,10 @@ def workload_config(wl, frames, gpus, **extra):
          "frames": frames, "points": frames * wl.points_per_frame, "cells": wl.cells,
          "sharding": f"frames split contiguously over {gpus} rank(s); NCCL int merge in finalize",
          "l2": "inputs larger than L2: each rank streams its resident point planes "
-               "(>= 800 MB at 8 ranks) once per step"}
+               "(>= 800 MB at 8 ranks) once per step",
+         "why_this_config": "BASELINE.json quotes the metric (>= 1e10 points/s on 8xB200, reported at 1/2/4/8 "
+                            "GPUs) on configs[2], the batched replay, and it fits one GPU (6.4 GB of points); "
+                            "configs[1] (one 262k-point scan, latency-bound) is measured under other_configs.C2"}
     c.update(extra)
     return c
 
