@@ -102,37 +102,51 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- CPU baseline
+class CpuOracle:
+    """Frame-parallel CPU pass of the oracle port (BASELINE.md variant 3): one private count grid per
+    thread, allocated ONCE here (outside every timed region), integer merge, one finalise."""
+
+    def __init__(self, wl, threads):
+        from oracle import gv_oracle as orc
+        self.wl, self.threads = wl, max(1, threads)
+        self.grids = [orc.Grid.from_cells(wl.grid_nx, wl.grid_ny, wl.resolution) for _ in range(self.threads)]
+
+    def run(self, xyz, boxes_per_frame):
+        """One pass over the frames in xyz ([3, F*P] numpy).  Returns seconds."""
+        from concurrent.futures import ThreadPoolExecutor
+
+        from grid_vision_b200 import synth
+        from oracle import gv_oracle as orc
+        wl, grids = self.wl, self.grids
+        P = wl.points_per_frame
+        F = xyz.shape[1] // P
+        Tc = synth.camera_extrinsics(1)[0]
+        Tb = synth.T_base_lidar()
+        K = wl.K()
+        threads = min(self.threads, F)
+
+        def work(t):
+            g = grids[t]
+            for f in range(t, F, threads):
+                fx = xyz[:, f * P:(f + 1) * P]
+                cx, cy, cz = orc.transform_points(Tc, fx[0], fx[1], fx[2])
+                lab, _, _, _ = orc.project_label(K, wl.image_w, wl.image_h, cx, cy, cz, boxes_per_frame[f])
+                g.accumulate(Tb, fx[0], fx[1], fx[2], lab, r_max=wl.r_max, want_cells=False)
+
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(threads) as ex:
+            list(ex.map(work, range(threads)))
+        for g in grids[1:threads]:
+            grids[0].hit += g.hit
+            grids[0].miss += g.miss
+            g.hit[:] = 0
+            g.miss[:] = 0
+        grids[0].finalize(F)
+        return time.perf_counter() - t0
+
+
 def cpu_oracle_run(wl, xyz, boxes_per_frame, threads):
-    """One pass of the oracle port over the frames in xyz ([3, F*P] numpy), frame-parallel with
-    private count grids and an integer merge (BASELINE.md variant 3).  Returns seconds."""
-    from concurrent.futures import ThreadPoolExecutor
-
-    from grid_vision_b200 import synth
-    from oracle import gv_oracle as orc
-    P = wl.points_per_frame
-    F = xyz.shape[1] // P
-    Tc = synth.camera_extrinsics(1)[0]
-    Tb = synth.T_base_lidar()
-    K = wl.K()
-    threads = max(1, min(threads, F))
-    grids = [orc.Grid.from_cells(wl.grid_nx, wl.grid_ny, wl.resolution) for _ in range(threads)]
-
-    def work(t):
-        g = grids[t]
-        for f in range(t, F, threads):
-            fx = xyz[:, f * P:(f + 1) * P]
-            cx, cy, cz = orc.transform_points(Tc, fx[0], fx[1], fx[2])
-            lab, _, _, _ = orc.project_label(K, wl.image_w, wl.image_h, cx, cy, cz, boxes_per_frame[f])
-            g.accumulate(Tb, fx[0], fx[1], fx[2], lab, r_max=wl.r_max, want_cells=False)
-
-    t0 = time.perf_counter()
-    with ThreadPoolExecutor(threads) as ex:
-        list(ex.map(work, range(threads)))
-    for g in grids[1:]:
-        grids[0].hit += g.hit
-        grids[0].miss += g.miss
-    grids[0].finalize(F)
-    return time.perf_counter() - t0
+    return CpuOracle(wl, threads).run(xyz, boxes_per_frame)
 
 
 def cpu_sample(wl, frames):
@@ -150,9 +164,10 @@ def run_reference_arm(args, wl):
     frames = max(2, min(2 * cores, 64))
     xyz, boxes = cpu_sample(wl, frames)
     pts = xyz.shape[1]
+    cpu = CpuOracle(wl, cores)
     for _ in range(max(1, min(args.warmup, 1))):
-        cpu_oracle_run(wl, xyz, boxes, cores)
-    ts = [cpu_oracle_run(wl, xyz, boxes, cores) for _ in range(args.steps)]
+        cpu.run(xyz, boxes)
+    ts = [cpu.run(xyz, boxes) for _ in range(args.steps)]
     t = float(np.mean(ts))
     v = pts / t
     sample = f"{frames} frames ({pts} points) of the workload per step, frame-parallel on {cores} threads"
@@ -450,7 +465,9 @@ def main():
             cores = os.cpu_count() or 1
             frames = max(2, min(2 * cores, 64))
             cx, cb = cpu_sample(wl, frames)
-            t = cpu_oracle_run(wl, cx, cb, cores)
+            cpu = CpuOracle(wl, cores)
+            cpu.run(cx, cb)  # warm-up (page-faults the private grids)
+            t = cpu.run(cx, cb)
             out["cpu_baseline"] = {"value": cx.shape[1] / t, "unit": UNIT, "cores": cores, "kind": "port",
                                    "sample": f"{frames} frames ({cx.shape[1]} points), frame-parallel oracle port, "
                                              f"{t:.2f} s"}
