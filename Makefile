@@ -12,8 +12,8 @@ LIBS      += -lnccl
 endif
 
 LIB := grid_vision_b200/lib/libgridvision_b200.so
-SRC := grid_vision_b200/csrc/gv_api.cu
-HDR := grid_vision_b200/csrc/gv_kernels.cuh include/gridvision_b200.h
+SRC := grid_vision_b200/csrc/gv_api.cu grid_vision_b200/csrc/gv_microbench.cu
+HDR := $(wildcard grid_vision_b200/csrc/*.cuh) include/gridvision_b200.h
 
 all: lib oracle
 

@@ -63,6 +63,7 @@ EXPORTS = [
     "gv_grid_to_occupancy",
     "gv_nccl_unique_id", "gv_nccl_init", "gv_nccl_world", "gv_grid_finalize_multi",
     "gv_ipc_export", "gv_ipc_import", "gv_ipc_close",
+    "gv_microbench_atomics",
 ]
 
 _lib = None

@@ -5,10 +5,12 @@
 // here: if no sm_100 device is usable gv_create fails and nothing else can be called.
 #include "gridvision_b200.h"
 #include "gv_kernels.cuh"
+#include "gv_points_fast.cuh"
 
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -31,7 +33,7 @@ enum {
   S_X, S_Y, S_Z, S_AOS, S_LAB, S_PIX, S_UV, S_BOX_RAW, S_BOX_F4, S_FRAME_OFF, S_BOX_OFF,
   S_TILE_PREFIX, S_TILE_START, S_TILE_END, S_TILE_BOX, S_CELL, S_FLAGS, S_FOOT_IN, S_FOOT_LAB,
   S_RECT, S_SMALL, S_OX, S_OY, S_OZ, S_SCAN0, S_SCAN1, S_SCAN2, S_SCAN3, S_UVZ, S_INDICES,
-  S_LABELS_IN, S_MASKS, S_SET_OFF, S_SWEEP, S_SWEEP_PREFIX, S_BATCH_ENTRY, S_BATCH_MI, S_BATCH_W, S_N2_TAB, S_N2_KEEP, S_N2_OUT, S_N2_OFF, S_N1_PLANES, S_N1_VALID, S_N1_SCORES, S_N1_STATE, S_COUNT
+  S_LABELS_IN, S_MASKS, S_SET_OFF, S_SWEEP, S_SWEEP_PREFIX, S_BATCH_ENTRY, S_BATCH_MI, S_BATCH_W, S_N2_TAB, S_N2_KEEP, S_N2_OUT, S_N2_OFF, S_N1_PLANES, S_N1_VALID, S_N1_SCORES, S_N1_STATE, S_DEFER, S_COUNT
 };
 
 constexpr size_t kPlanePad = 4096;  // slack cells so multi-GPU slabs can be equal-sized
@@ -62,6 +64,8 @@ struct gv_ctx {
   int n_sweep = 0;
   unsigned n_sweep_items = 0;
   bool counts_dirty = false, ends_dirty = false;
+  bool use_fast = true;  // $GV_NO_FAST=1 forces the generic k_points (A/B measurements)
+  int fast_unroll = 2;   // $GV_FAST_U: points per thread per iteration of k_points_fast
 
   bool has_base = false;
   float Tb[16];
@@ -387,7 +391,7 @@ int fuse_dev_impl(gv_ctx *ctx, const float *d_x, const float *d_y, const float *
     int sh, tx, ty;
     mask_geometry(a.cam[c].W, a.cam[c].H, &sh, &tx, &ty);
     k_box_masks<<<1, kThreads, 0, ctx->stream>>>(d_f4, d_set_off + c, sh, tx, ty, a.mask_words,
-                                                 a.mask_stride, d_masks + (size_t)c * a.mask_stride);
+                                                 a.mask_stride, 0, d_masks + (size_t)c * a.mask_stride);
     GV_LAUNCH_CHECK();
   }
   GV_CUDA(cudaStreamSynchronize(ctx->stream));  // set_off is a host temporary
@@ -764,6 +768,8 @@ int gv_create(gv_ctx **out, int device)
   }
   ctx->stream = ctx->own_stream;
   ctx->timing = std::getenv("GV_TIMING") != nullptr;
+  ctx->use_fast = std::getenv("GV_NO_FAST") == nullptr;
+  if (const char *u = std::getenv("GV_FAST_U")) ctx->fast_unroll = std::atoi(u);
   *out = ctx;
   return GV_OK;
 }
@@ -1435,6 +1441,127 @@ int gv_grid_finalize(gv_ctx *ctx, int32_t k_decay, const double *corners, int nf
   return finalize_impl(ctx, k_decay, corners, nullptr, nfoot, 0);
 }
 
+// ---- k_points_fast (gv_points_fast.cuh): eligibility, parameter block, launch ------------
+static bool fast_eligible(const gv_ctx *ctx, const BinDev &bin, int max_boxes)
+{
+  const CamDev &c = ctx->cam[0];
+  if (!(ctx->use_fast && c.has_T && c.t_small && c.canon && bin.t_small && bin.fast_index_ok &&
+        bin.origin_ok && max_boxes <= kFastBoxes))
+    return false;
+  // operand ranges of the inlined IEEE division / square-root sequences (div_rn_inrange,
+  // sqrt_rn_inrange): the sensor origin is at least 2^-20 cells away from every map edge (so the
+  // clip numerators and denominators are normal numbers) and the range cap is a sane length
+  const float lim = 9.5367431640625e-07f;  // 2^-20
+  const float nxf = (float)bin.g.nx, nyf = (float)bin.g.ny;
+  if (!(bin.oaxf >= lim && bin.oayf >= lim && nxf - bin.oaxf >= lim && nyf - bin.oayf >= lim)) return false;
+  if (bin.cap && !(bin.rmaxf >= 1.0e-3f && bin.rmaxf <= 1.0e6f)) return false;
+  return true;
+}
+
+static void fill_fast_args(const PointArgs &a, unsigned *d_defer, FastArgs &f, bool *bounded)
+{
+  memset(&f, 0, sizeof(f));
+  const CamDev &c = a.cam[0];
+  const BinDev &b = a.bin;
+  f.x = a.x; f.y = a.y; f.z = a.z;
+  f.labels = a.labels;
+  f.ends = a.ends;
+  f.defer_bits = d_defer;
+  f.boxes = a.boxes;
+  f.masks = a.masks;
+  f.tile_start = a.tile_start; f.tile_end = a.tile_end; f.tile_boxes = a.tile_boxes;
+  f.tile0 = a.tile0;
+  f.tile_pts = a.tile_pts;
+  f.mask_stride = a.mask_stride;
+  f.mask_shift = a.mask_shift[0];
+  f.mask_tx = a.mask_tx[0];
+  for (int i = 0; i < 12; ++i) { f.Tc[i] = c.T[i]; f.Tb[i] = b.T[i]; }
+  f.fx = c.fxf; f.fy = c.fyf; f.cx = c.cxf; f.cy = c.cyf;
+  // E(q) = 2^-22 (6|q| + 1.5|c| + 1), see fast_point
+  const float u22 = 2.384185791015625e-07f;
+  f.e6 = 6.0f * u22;
+  f.e0u = u22 * (1.5f * std::fabs(c.cxf) + 1.0f) * 1.0001f;
+  f.e0v = u22 * (1.5f * std::fabs(c.cyf) + 1.0f) * 1.0001f;
+  f.Wf = c.Wf; f.Hf = c.Hf;
+  f.oxf = b.oxf; f.oyf = b.oyf;
+  f.rmaxf = b.rmaxf;
+  f.rmax2f = b.cap ? b.rmax2f : INFINITY;
+  f.lab_min = b.occ_mode == 1 ? 0 : -1;
+  f.z_min = b.z_min; f.z_max = b.z_max;
+  // index FMA: r = p * (-1/res) + (c0/res + bias + 1.5*2^36); ulp(r) = 2^-16 cells
+  const GridGeom &g = b.g;
+  const int nmax = g.nx > g.ny ? g.nx : g.ny;
+  int bias_cells = 16;
+  *bounded = false;
+  if (b.cap) {
+    const double reach = std::ceil((double)b.rmaxf / g.res) + 4.0;  // cells a beam can extend from the origin
+    if (reach + (double)nmax + reach < 32768.0) {
+      bias_cells = (int)reach;
+      *bounded = true;
+    }
+  }
+  const double magic = 103079215104.0;  // 1.5 * 2^36
+  f.nires = -1.0 / g.res;
+  f.Cx = b.c0xd / g.res + (double)bias_cells + magic;
+  f.Cy = b.c0yd / g.res + (double)bias_cells + magic;
+  f.kbias = (unsigned)bias_cells << 16;
+  f.hi0 = 0x42380000u;
+  f.klim_x = (unsigned)g.nx << 16;
+  f.klim_y = (unsigned)g.ny << 16;
+  f.nx = g.nx;
+  f.ny = g.ny;
+  // clip geometry: the same single-rounded float expressions as clip_end / oracle gvo_clip_end
+  f.c0xf = b.c0xf; f.c0yf = b.c0yf; f.inv_resf = b.inv_resf;
+  f.oaxf = b.oaxf; f.oayf = b.oayf;
+  f.nxf = (float)g.nx; f.nyf = (float)g.ny;
+  f.noaxf = 0.0f - b.oaxf; f.noayf = 0.0f - b.oayf;
+  f.paxf = f.nxf - b.oaxf; f.payf = f.nyf - b.oayf;
+  f.cam = c;
+  f.bin = b;
+}
+
+static int launch_points_fast(gv_ctx *ctx, FastArgs &f, bool bounded, unsigned tile0, unsigned ntiles)
+{
+  if (ntiles == 0) return GV_OK;
+  f.tile0 = tile0;
+  f.ntiles = ntiles;
+  const size_t smem = (size_t)f.mask_stride * sizeof(unsigned long long);
+  const bool lab = f.labels != nullptr, zg = f.bin.use_z_gate != 0;
+  const int U = ctx->fast_unroll;
+#define GV_FAST_LAUNCH(UU, BB, LL, ZZ) k_points_fast<UU, BB, LL, ZZ><<<ntiles, kThreads, smem, ctx->stream>>>(f)
+  if (zg) {  // rare configuration: one instantiation per remaining flag
+    if (bounded && lab) GV_FAST_LAUNCH(2, true, true, true);
+    else if (bounded) GV_FAST_LAUNCH(2, true, false, true);
+    else if (lab) GV_FAST_LAUNCH(2, false, true, true);
+    else GV_FAST_LAUNCH(2, false, false, true);
+  } else if (U == 1) {
+    if (bounded && lab) GV_FAST_LAUNCH(1, true, true, false);
+    else if (bounded) GV_FAST_LAUNCH(1, true, false, false);
+    else if (lab) GV_FAST_LAUNCH(1, false, true, false);
+    else GV_FAST_LAUNCH(1, false, false, false);
+  } else if (U == 4) {
+    if (bounded && lab) GV_FAST_LAUNCH(4, true, true, false);
+    else if (bounded) GV_FAST_LAUNCH(4, true, false, false);
+    else if (lab) GV_FAST_LAUNCH(4, false, true, false);
+    else GV_FAST_LAUNCH(4, false, false, false);
+  } else {
+    if (bounded && lab) GV_FAST_LAUNCH(2, true, true, false);
+    else if (bounded) GV_FAST_LAUNCH(2, true, false, false);
+    else if (lab) GV_FAST_LAUNCH(2, false, true, false);
+    else GV_FAST_LAUNCH(2, false, false, false);
+  }
+#undef GV_FAST_LAUNCH
+  GV_LAUNCH_CHECK();
+  // the points whose decisions could not be certified (a ballot-word bitmap, normally < 0.1 %)
+  const unsigned long long nwords = (unsigned long long)ntiles * (unsigned)(f.tile_pts >> 5);
+  unsigned nb = (unsigned)((nwords + kThreads - 1) / kThreads);
+  const unsigned cap = (unsigned)ctx->num_sms * 16u;
+  if (nb > cap) nb = cap;
+  k_points_deferred<<<nb, kThreads, 0, ctx->stream>>>(f);
+  GV_LAUNCH_CHECK();
+  return GV_OK;
+}
+
 // ---- batch: the whole hot path, one kernel pass over the points ------------------------
 static int process_batch_impl(gv_ctx *ctx, const float *px, const float *py, const float *pz,
                               bool points_on_device, const uint64_t *frame_offsets, int nframes,
@@ -1540,8 +1667,10 @@ static int process_batch_impl(gv_ctx *ctx, const float *px, const float *py, con
   a.smem_boxes = max_boxes;
   unsigned long long *d_masks = nullptr;
   GV_TRY(reserve_t(ctx, S_MASKS, (size_t)nframes * a.mask_stride, &d_masks));
+  const bool fast = fast_eligible(ctx, a.bin, max_boxes);
   k_box_masks<<<nframes, kThreads, 0, ctx->stream>>>(d_f4, d_boff, a.mask_shift[0], a.mask_tx[0],
-                                                    mty, a.mask_words, a.mask_stride, d_masks);
+                                                    mty, a.mask_words, a.mask_stride, fast ? 1 : 0,
+                                                    d_masks);
   GV_LAUNCH_CHECK();
   a.masks = d_masks;
   a.tile_pts = tile_pts;
@@ -1568,8 +1697,23 @@ static int process_batch_impl(gv_ctx *ctx, const float *px, const float *py, con
     GV_CUDA(cudaFuncSetAttribute(k_points<true, true, false, false, false>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
+  FastArgs fa;
+  bool bounded = false;
+  if (fast) {
+    // ballot-word bitmap of deferred points: all-zero between launches (k_points_deferred clears
+    // what k_points_fast set), so it is zeroed only when the slot is (re)allocated
+    const size_t nwords = (size_t)ntiles * (size_t)(tile_pts >> 5);
+    unsigned *d_defer = nullptr;
+    const void *before = ctx->s[S_DEFER].p;
+    const size_t cap_before = ctx->s[S_DEFER].cap;
+    GV_TRY(reserve_t(ctx, S_DEFER, nwords, &d_defer));
+    if (ctx->s[S_DEFER].p != before || ctx->s[S_DEFER].cap != cap_before)
+      GV_CUDA(cudaMemsetAsync(d_defer, 0, ctx->s[S_DEFER].cap, ctx->stream));
+    fill_fast_args(a, d_defer, fa, &bounded);
+  }
   if (points_on_device) {
     a.tile0 = 0;
+    if (fast) return launch_points_fast(ctx, fa, bounded, 0, ntiles);
     return launch_points(ctx, true, true, a, ntiles, smem);
   }
 
@@ -1596,7 +1740,11 @@ static int process_batch_impl(gv_ctx *ctx, const float *px, const float *py, con
     GV_CUDA(cudaEventRecord(e_h2d, ctx->h2d_stream));
     GV_CUDA(cudaStreamWaitEvent(ctx->stream, e_h2d, 0));
     a.tile0 = tile_prefix[f0];
-    GV_TRY(launch_points(ctx, true, true, a, tile_prefix[f1] - tile_prefix[f0], smem));
+    if (fast) {
+      GV_TRY(launch_points_fast(ctx, fa, bounded, a.tile0, tile_prefix[f1] - tile_prefix[f0]));
+    } else {
+      GV_TRY(launch_points(ctx, true, true, a, tile_prefix[f1] - tile_prefix[f0], smem));
+    }
     if (labels_out && c1 > c0) {
       GV_CUDA(cudaEventRecord(e_k, ctx->stream));
       GV_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, e_k, 0));

@@ -576,10 +576,12 @@ __global__ void __launch_bounds__(kThreads) k_points(const __grid_constant__ Poi
 // A point with float pixel (u,v) lies in tile ((int)u >> shift, (int)v >> shift), and a box
 // contains it only if x_min <= u <= x_max, so boxes outside the mask can never match; the
 // test is conservative, never lossy.  NaN bounds compare false everywhere -> bit clear.
+// rev32: bit (31 - b%32) of 32-bit half (b%64)/32 instead of bit b%64, so that a count-leading-
+// zeros walk visits boxes in ascending order (k_points_fast).
 __global__ void __launch_bounds__(kThreads) k_box_masks(const float4 *__restrict__ boxes,
                                                         const int *__restrict__ set_offsets,
                                                         int shift, int tiles_x, int tiles_y,
-                                                        int words, int stride,
+                                                        int words, int stride, int rev32,
                                                         unsigned long long *__restrict__ masks)
 {
   const int set = blockIdx.x;
@@ -593,7 +595,8 @@ __global__ void __launch_bounds__(kThreads) k_box_masks(const float4 *__restrict
     const int bw1 = bw0 + 64 < b1 ? bw0 + 64 : b1;
     for (int b = bw0; b < bw1; ++b) {
       const float4 B = boxes[b];
-      if (B.z >= x0 && B.x < x0 + S && B.w >= y0 && B.y < y0 + S) m |= 1ull << (b - bw0);
+      const int bit = rev32 ? ((b - bw0) & 32) + 31 - ((b - bw0) & 31) : b - bw0;
+      if (B.z >= x0 && B.x < x0 + S && B.w >= y0 && B.y < y0 + S) m |= 1ull << bit;
     }
     masks[(size_t)set * stride + t] = m;
   }

@@ -285,6 +285,17 @@ GV_API int gv_ipc_import(gv_ctx *ctx, const void *blobs, int world, int rank);
 /* unmap the peers again: gv_grid_finalize_multi goes back to the NCCL collectives */
 GV_API int gv_ipc_close(gv_ctx *ctx);
 
+/* -------------------------------------------------------------- measurement --- */
+/* Atomic-throughput ceilings of this device for the two atomic-bound kernels (the
+ * raycast's cells/s is reported beside "RED.global to L2-resident lines" and "atomicAdd int32 to
+ * shared, conflict-free").  Not part of the hot path and has no reference counterpart; bench.py
+ * calls it to express k_sweep_walk / k_points atomic rates as fractions of a measured peak.
+ * kind 0: RED.64 global, 1: RED.32 global, 2: shared int32 atomicAdd (conflict-free).
+ * pattern (global kinds): 0 spread, 1 32 consecutive cells, 2 32 cells `stride` apart,
+ * 3 runs of 4 lanes per cell, 4 one cell per warp.  ncells_pow2 cells of 8 bytes are allocated. */
+GV_API int gv_microbench_atomics(int device, int kind, int pattern, size_t ncells_pow2,
+                                 unsigned stride, int reps, double *ops_per_s_out);
+
 #ifdef __cplusplus
 }
 #endif

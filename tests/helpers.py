@@ -50,3 +50,28 @@ def rel_close(a, b, rtol=1e-5):
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
     return np.all(np.abs(a - b) <= rtol * np.maximum(np.abs(a), np.abs(b)))
+
+
+def oracle_batch(wl, xyz, fo, per_frame_boxes, T_cam, T_base, threads=8, **prm):
+    """Frame-parallel oracle pass over a batch (per-thread private count grids, exact integer
+    merge): returns (labels int16 [n], merged Grid).  prm: occ_mode / z_gate / r_max."""
+    from concurrent.futures import ThreadPoolExecutor
+    nframes = len(fo) - 1
+    threads = max(1, min(threads, nframes))
+    grids = [oracle_grid(wl) for _ in range(threads)]
+    labels = np.full(int(fo[-1]), -9, np.int16)
+
+    def work(t):
+        for f in range(t, nframes, threads):
+            s, e = int(fo[f]), int(fo[f + 1])
+            fx = xyz[:, s:e]
+            lab, _, _, _ = oracle_fuse(wl, fx, per_frame_boxes[f], T_cam)
+            labels[s:e] = lab
+            grids[t].accumulate(T_base, *fx, lab, want_cells=False, **prm)
+
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(work, range(threads)))
+    for g in grids[1:]:
+        grids[0].hit += g.hit
+        grids[0].miss += g.miss
+    return labels, grids[0]
