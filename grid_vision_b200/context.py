@@ -77,10 +77,14 @@ class Context:
         self._check(self._lib.gv_synchronize(self._h), "gv_synchronize")
 
     def use_torch_stream(self):
-        """Launch on torch's current stream so torch.cuda.Event brackets the kernels."""
+        """Launch on torch's current stream (ordering with the tensors' producers/consumers, and
+        torch.cuda.Event brackets the kernels).  Called automatically by every method that takes
+        torch CUDA tensors; re-binding happens only when torch's current stream changed."""
         import torch
         s = torch.cuda.current_stream(self.device).cuda_stream
-        self._check(self._lib.gv_set_stream(self._h, C.c_void_p(s)), "gv_set_stream")
+        if getattr(self, "_bound_stream", None) != s:
+            self._check(self._lib.gv_set_stream(self._h, C.c_void_p(s)), "gv_set_stream")
+            self._bound_stream = s
 
     def stats(self) -> dict:
         st = Stats()
@@ -131,6 +135,7 @@ class Context:
                  uv=None, is_dense=False):
         """torch CUDA tensors in/out; d_boxes is a uint8 CUDA tensor holding 40-byte records."""
         off = None if box_cam_offsets is None else _np(box_cam_offsets, np.int32)
+        self.use_torch_stream()
         self._check(self._lib.gv_fuse_dev(self._h, _dptr(x), _dptr(y), _dptr(z),
                                           C.c_size_t(x.numel()), C.c_int(int(is_dense)),
                                           _dptr(d_boxes), C.c_int(nboxes), _ptr(off),
@@ -269,6 +274,7 @@ class Context:
                         want_cells=True):
         params = params or accum_params()
         if _is_torch(x):
+            self.use_torch_stream()
             self._check(self._lib.gv_grid_accumulate_dev(
                 self._h, _dptr(x), _dptr(y), _dptr(z), C.c_size_t(x.numel()), _dptr(labels),
                 C.byref(params), None, None), "gv_grid_accumulate_dev")
@@ -303,6 +309,7 @@ class Context:
         nf = len(fo) - 1
         assert len(bo) == nf + 1
         if _is_torch(x):
+            self.use_torch_stream()
             self._check(self._lib.gv_process_batch_dev(
                 self._h, _dptr(x), _dptr(y), _dptr(z), _ptr(fo), C.c_int(nf), _dptr(boxes),
                 _ptr(bo), C.byref(params), _dptr(labels_out)), "gv_process_batch_dev")

@@ -43,6 +43,9 @@ constexpr size_t kPlanePad = 4096;  // slack cells so multi-GPU slabs can be equ
 struct gv_ctx {
   int device = 0;
   int num_sms = 148;
+  size_t max_smem_optin = 48 * 1024;  // cudaDevAttrMaxSharedMemoryPerBlockOptin
+  size_t persist_bytes = 0;           // persisting-L2 carve-out this context asked for
+  size_t max_window = 0;              // cudaDeviceProp::accessPolicyMaxWindowSize
   cudaStream_t stream = nullptr;
   cudaStream_t own_stream = nullptr;
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
@@ -64,8 +67,12 @@ struct gv_ctx {
   int n_sweep = 0;
   unsigned n_sweep_items = 0;
   bool counts_dirty = false, ends_dirty = false;
+  bool multi_checked = false;  // ranks verified to share geometry + pose (gv_grid_finalize_multi)
   bool use_fast = true;  // $GV_NO_FAST=1 forces the generic k_points (A/B measurements)
   int fast_unroll = 2;   // $GV_FAST_U: points per thread per iteration of k_points_fast
+  bool use_tma = true;   // $GV_NO_TMA=1: k_points_fast (per-tile CTAs, LDG) instead of k_points_tma
+  int fast_agg = 1;      // $GV_FAST_AGG: 0 one RED per beam, 1 match-any groups, 2 adjacent runs
+  bool l2_persist = true;  // $GV_L2_PERSIST=0: no persisting-L2 window on the end-cell plane
 
   bool has_base = false;
   float Tb[16];
@@ -398,6 +405,9 @@ int fuse_dev_impl(gv_ctx *ctx, const float *d_x, const float *d_y, const float *
   a.masks = d_masks;
   const size_t smem = (size_t)a.smem_boxes * sizeof(float4) +
                       (size_t)ctx->ncam * a.mask_stride * sizeof(unsigned long long);
+  GV_REQUIRE(smem <= ctx->max_smem_optin, GV_ERR_INVALID,
+             "%d boxes need %zu bytes of shared memory for the box/tile-mask stage; this device allows %zu "
+             "(about 14000 boxes per call)", nboxes, smem, ctx->max_smem_optin);
   if (smem > 48 * 1024) {
     GV_CUDA(cudaFuncSetAttribute(k_points<true, false, false, false, false>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -630,6 +640,7 @@ void free_grid(gv_ctx *ctx)
 
 int refresh_origin(gv_ctx *ctx)
 {
+  ctx->multi_checked = false;
   // start cell + continuous index coordinates of the sensor origin, computed by the same
   // device getIndex every beam uses
   if (!(ctx->has_grid && ctx->has_base)) return GV_OK;
@@ -755,6 +766,7 @@ int gv_create(gv_ctx **out, int device)
   if (!ctx) return GV_ERR_INVALID;
   ctx->device = device;
   ctx->num_sms = prop.multiProcessorCount;
+  ctx->max_smem_optin = prop.sharedMemPerBlockOptin;
   if (cudaSetDevice(device) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -770,6 +782,20 @@ int gv_create(gv_ctx **out, int device)
   ctx->timing = std::getenv("GV_TIMING") != nullptr;
   ctx->use_fast = std::getenv("GV_NO_FAST") == nullptr;
   if (const char *u = std::getenv("GV_FAST_U")) ctx->fast_unroll = std::atoi(u);
+  if (const char *u = std::getenv("GV_FAST_AGG")) ctx->fast_agg = std::atoi(u);
+  ctx->use_tma = std::getenv("GV_NO_TMA") == nullptr;
+  if (const char *u = std::getenv("GV_L2_PERSIST")) ctx->l2_persist = std::atoi(u) != 0;
+  if (ctx->l2_persist && prop.persistingL2CacheMaxSize > 0) {
+    // room for the end-cell plane of a 2048 x 2048 map (32 MiB) plus slack; larger planes get a
+    // proportional hit ratio (set_ends_window)
+    size_t want = (size_t)48 << 20;
+    if (want > (size_t)prop.persistingL2CacheMaxSize) want = (size_t)prop.persistingL2CacheMaxSize;
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+      ctx->persist_bytes = want;
+      ctx->max_window = (size_t)prop.accessPolicyMaxWindowSize;
+    }
+    cudaGetLastError();
+  }
   *out = ctx;
   return GV_OK;
 }
@@ -1441,6 +1467,27 @@ int gv_grid_finalize(gv_ctx *ctx, int32_t k_decay, const double *corners, int nf
   return finalize_impl(ctx, k_decay, corners, nullptr, nfoot, 0);
 }
 
+// Persisting-L2 access window on the end-cell plane for the kernels launched next on the context
+// stream: every beam's RED wants its line in L2, while the point planes stream through the same
+// cache (ncu, round 2: half of the RED sectors missed L2 without it).  on = false clears it.
+static void set_ends_window(gv_ctx *ctx, bool on)
+{
+  if (!ctx->persist_bytes || !ctx->max_window) return;
+  cudaStreamAttrValue v;
+  memset(&v, 0, sizeof(v));
+  if (on) {
+    size_t bytes = ctx->ncells * sizeof(unsigned long long);
+    if (bytes > ctx->max_window) bytes = ctx->max_window;
+    v.accessPolicyWindow.base_ptr = ctx->d_ends;
+    v.accessPolicyWindow.num_bytes = bytes;
+    v.accessPolicyWindow.hitRatio = bytes <= ctx->persist_bytes ? 1.0f : (float)ctx->persist_bytes / (float)bytes;
+    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  }
+  cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &v);
+  cudaGetLastError();  // a hint: failure to set it changes nothing but speed
+}
+
 // ---- k_points_fast (gv_points_fast.cuh): eligibility, parameter block, launch ------------
 static bool fast_eligible(const gv_ctx *ctx, const BinDev &bin, int max_boxes)
 {
@@ -1463,6 +1510,7 @@ static void fill_fast_args(const PointArgs &a, unsigned *d_defer, FastArgs &f, b
   memset(&f, 0, sizeof(f));
   const CamDev &c = a.cam[0];
   const BinDev &b = a.bin;
+  FastHot &h = f.hot;
   f.x = a.x; f.y = a.y; f.z = a.z;
   f.labels = a.labels;
   f.ends = a.ends;
@@ -1475,18 +1523,20 @@ static void fill_fast_args(const PointArgs &a, unsigned *d_defer, FastArgs &f, b
   f.mask_stride = a.mask_stride;
   f.mask_shift = a.mask_shift[0];
   f.mask_tx = a.mask_tx[0];
-  for (int i = 0; i < 12; ++i) { f.Tc[i] = c.T[i]; f.Tb[i] = b.T[i]; }
-  f.fx = c.fxf; f.fy = c.fyf; f.cx = c.cxf; f.cy = c.cyf;
+  for (int i = 0; i < 12; ++i) h.Tc[i] = c.T[i];
+  for (int i = 0; i < 8; ++i) h.Tb[i] = b.T[i];
+  for (int i = 0; i < 4; ++i) f.Tbz[i] = b.T[8 + i];
+  h.fx = c.fxf; h.fy = c.fyf; h.cx = c.cxf; h.cy = c.cyf;
   // E(q) = 2^-22 (6|q| + 1.5|c| + 1), see fast_point
   const float u22 = 2.384185791015625e-07f;
-  f.e6 = 6.0f * u22;
-  f.e0u = u22 * (1.5f * std::fabs(c.cxf) + 1.0f) * 1.0001f;
-  f.e0v = u22 * (1.5f * std::fabs(c.cyf) + 1.0f) * 1.0001f;
-  f.Wf = c.Wf; f.Hf = c.Hf;
-  f.oxf = b.oxf; f.oyf = b.oyf;
-  f.rmaxf = b.rmaxf;
-  f.rmax2f = b.cap ? b.rmax2f : INFINITY;
-  f.lab_min = b.occ_mode == 1 ? 0 : -1;
+  h.e6 = 6.0f * u22;
+  h.e0u = u22 * (1.5f * std::fabs(c.cxf) + 1.0f) * 1.0001f;
+  h.e0v = u22 * (1.5f * std::fabs(c.cyf) + 1.0f) * 1.0001f;
+  h.Wf = c.Wf; h.Hf = c.Hf;
+  h.oxf = b.oxf; h.oyf = b.oyf;
+  h.rmaxf = b.rmaxf;
+  h.rmax2f = b.cap ? b.rmax2f : INFINITY;
+  h.lab_min = b.occ_mode == 1 ? 0 : -1;
   f.z_min = b.z_min; f.z_max = b.z_max;
   // index FMA: r = p * (-1/res) + (c0/res + bias + 1.5*2^36); ulp(r) = 2^-16 cells
   const GridGeom &g = b.g;
@@ -1501,14 +1551,16 @@ static void fill_fast_args(const PointArgs &a, unsigned *d_defer, FastArgs &f, b
     }
   }
   const double magic = 103079215104.0;  // 1.5 * 2^36
-  f.nires = -1.0 / g.res;
-  f.Cx = b.c0xd / g.res + (double)bias_cells + magic;
-  f.Cy = b.c0yd / g.res + (double)bias_cells + magic;
-  f.kbias = (unsigned)bias_cells << 16;
+  h.nires = -1.0 / g.res;
+  h.Cx = b.c0xd / g.res + (double)bias_cells + magic;
+  h.Cy = b.c0yd / g.res + (double)bias_cells + magic;
+  h.kbias = (unsigned)bias_cells << 16;
   f.hi0 = 0x42380000u;
   f.klim_x = (unsigned)g.nx << 16;
   f.klim_y = (unsigned)g.ny << 16;
-  f.nx = g.nx;
+  h.klim_x16 = f.klim_x - 16u;
+  h.klim_y16 = f.klim_y - 16u;
+  h.nx = g.nx;
   f.ny = g.ny;
   // clip geometry: the same single-rounded float expressions as clip_end / oracle gvo_clip_end
   f.c0xf = b.c0xf; f.c0yf = b.c0yf; f.inv_resf = b.inv_resf;
@@ -1520,39 +1572,66 @@ static void fill_fast_args(const PointArgs &a, unsigned *d_defer, FastArgs &f, b
   f.bin = b;
 }
 
-static int launch_points_fast(gv_ctx *ctx, FastArgs &f, bool bounded, unsigned tile0, unsigned ntiles)
+// tma: k_points_tma (persistent, bulk-copy fed) instead of k_points_fast
+static int launch_points_fast(gv_ctx *ctx, FastArgs &f, bool bounded, bool tma, unsigned tile0, unsigned ntiles)
 {
   if (ntiles == 0) return GV_OK;
   f.tile0 = tile0;
   f.ntiles = ntiles;
-  const size_t smem = (size_t)f.mask_stride * sizeof(unsigned long long);
   const bool lab = f.labels != nullptr, zg = f.bin.use_z_gate != 0;
-  const int U = ctx->fast_unroll;
-#define GV_FAST_LAUNCH(UU, BB, LL, ZZ) k_points_fast<UU, BB, LL, ZZ><<<ntiles, kThreads, smem, ctx->stream>>>(f)
-  if (zg) {  // rare configuration: one instantiation per remaining flag
-    if (bounded && lab) GV_FAST_LAUNCH(2, true, true, true);
-    else if (bounded) GV_FAST_LAUNCH(2, true, false, true);
-    else if (lab) GV_FAST_LAUNCH(2, false, true, true);
-    else GV_FAST_LAUNCH(2, false, false, true);
-  } else if (U == 1) {
-    if (bounded && lab) GV_FAST_LAUNCH(1, true, true, false);
-    else if (bounded) GV_FAST_LAUNCH(1, true, false, false);
-    else if (lab) GV_FAST_LAUNCH(1, false, true, false);
-    else GV_FAST_LAUNCH(1, false, false, false);
-  } else if (U == 4) {
-    if (bounded && lab) GV_FAST_LAUNCH(4, true, true, false);
-    else if (bounded) GV_FAST_LAUNCH(4, true, false, false);
-    else if (lab) GV_FAST_LAUNCH(4, false, true, false);
-    else GV_FAST_LAUNCH(4, false, false, false);
+  const int U = ctx->fast_unroll, G = ctx->fast_agg;
+  if (tma) {
+    const size_t stage = 3 * (size_t)f.tile_pts * 4 + kFastBoxes * 16 + (size_t)f.mask_stride * 8;
+    const size_t smem = 2 * stage;
+    unsigned grid = 2u * (unsigned)ctx->num_sms;
+    if (grid > ntiles) grid = ntiles;
+#define GV_TMA_LAUNCH(UU, BB, LL, ZZ, GG)                                                            \
+  do {                                                                                               \
+    GV_CUDA(cudaFuncSetAttribute(k_points_tma<UU, BB, LL, ZZ, GG>,                                    \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
+    k_points_tma<UU, BB, LL, ZZ, GG><<<grid, kThreads, smem, ctx->stream>>>(f);                       \
+  } while (0)
+#define GV_TMA_BL(UU, ZZ, GG)                                  \
+  do {                                                         \
+    if (bounded && lab) GV_TMA_LAUNCH(UU, true, true, ZZ, GG); \
+    else if (bounded) GV_TMA_LAUNCH(UU, true, false, ZZ, GG);  \
+    else if (lab) GV_TMA_LAUNCH(UU, false, true, ZZ, GG);      \
+    else GV_TMA_LAUNCH(UU, false, false, ZZ, GG);              \
+  } while (0)
+    if (zg) GV_TMA_BL(2, true, 1);
+    else if (G == 0 && U == 1) GV_TMA_BL(1, false, 0);
+    else if (G == 0) GV_TMA_BL(2, false, 0);
+    else if (G == 2 && U == 1) GV_TMA_BL(1, false, 2);
+    else if (G == 2) GV_TMA_BL(2, false, 2);
+    else if (U == 1) GV_TMA_BL(1, false, 1);
+    else GV_TMA_BL(2, false, 1);
+#undef GV_TMA_BL
+#undef GV_TMA_LAUNCH
   } else {
-    if (bounded && lab) GV_FAST_LAUNCH(2, true, true, false);
-    else if (bounded) GV_FAST_LAUNCH(2, true, false, false);
-    else if (lab) GV_FAST_LAUNCH(2, false, true, false);
-    else GV_FAST_LAUNCH(2, false, false, false);
-  }
+    const size_t smem = (size_t)f.mask_stride * sizeof(unsigned long long);
+#define GV_FAST_LAUNCH(UU, BB, LL, ZZ, GG) k_points_fast<UU, BB, LL, ZZ, GG><<<ntiles, kThreads, smem, ctx->stream>>>(f)
+#define GV_FAST_BL(UU, ZZ, GG)                                  \
+  do {                                                          \
+    if (bounded && lab) GV_FAST_LAUNCH(UU, true, true, ZZ, GG); \
+    else if (bounded) GV_FAST_LAUNCH(UU, true, false, ZZ, GG);  \
+    else if (lab) GV_FAST_LAUNCH(UU, false, true, ZZ, GG);      \
+    else GV_FAST_LAUNCH(UU, false, false, ZZ, GG);              \
+  } while (0)
+    if (zg) GV_FAST_BL(2, true, 1);  // rare configuration: one instantiation per remaining flag
+    else if (G == 0 && U == 1) GV_FAST_BL(1, false, 0);
+    else if (G == 0 && U == 4) GV_FAST_BL(4, false, 0);
+    else if (G == 0) GV_FAST_BL(2, false, 0);
+    else if (G == 2 && U == 1) GV_FAST_BL(1, false, 2);
+    else if (G == 2 && U == 4) GV_FAST_BL(4, false, 2);
+    else if (G == 2) GV_FAST_BL(2, false, 2);
+    else if (U == 1) GV_FAST_BL(1, false, 1);
+    else if (U == 4) GV_FAST_BL(4, false, 1);
+    else GV_FAST_BL(2, false, 1);
+#undef GV_FAST_BL
 #undef GV_FAST_LAUNCH
+  }
   GV_LAUNCH_CHECK();
-  // the points whose decisions could not be certified (a ballot-word bitmap, normally < 0.1 %)
+  // the points whose decisions could not be certified (a bitmap, normally < 0.1 % of the points)
   const unsigned long long nwords = (unsigned long long)ntiles * (unsigned)(f.tile_pts >> 5);
   unsigned nb = (unsigned)((nwords + kThreads - 1) / kThreads);
   const unsigned cap = (unsigned)ctx->num_sms * 16u;
@@ -1663,7 +1742,7 @@ static int process_batch_impl(gv_ctx *ctx, const float *px, const float *py, con
   int mty;
   mask_geometry(ctx->cam[0].W, ctx->cam[0].H, &a.mask_shift[0], &a.mask_tx[0], &mty);
   a.mask_words = (max_boxes + 63) / 64;
-  a.mask_stride = a.mask_tx[0] * mty * a.mask_words;
+  a.mask_stride = (a.mask_tx[0] * mty * a.mask_words + 1) & ~1;  // even: 16-byte sets (bulk copies)
   a.smem_boxes = max_boxes;
   unsigned long long *d_masks = nullptr;
   GV_TRY(reserve_t(ctx, S_MASKS, (size_t)nframes * a.mask_stride, &d_masks));
@@ -1693,12 +1772,15 @@ static int process_batch_impl(gv_ctx *ctx, const float *px, const float *py, con
   ctx->ends_dirty = true;
   const size_t smem = (size_t)max_boxes * sizeof(float4) +
                       (size_t)a.mask_stride * sizeof(unsigned long long);
+  GV_REQUIRE(smem <= ctx->max_smem_optin, GV_ERR_INVALID,
+             "a frame with %d boxes needs %zu bytes of shared memory for the box/tile-mask stage; this "
+             "device allows %zu (about 4700 boxes per frame)", max_boxes, smem, ctx->max_smem_optin);
   if (smem > 48 * 1024)
     GV_CUDA(cudaFuncSetAttribute(k_points<true, true, false, false, false>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
   FastArgs fa;
-  bool bounded = false;
+  bool bounded = false, tma = false;
   if (fast) {
     // ballot-word bitmap of deferred points: all-zero between launches (k_points_deferred clears
     // what k_points_fast set), so it is zeroed only when the slot is (re)allocated
@@ -1710,12 +1792,22 @@ static int process_batch_impl(gv_ctx *ctx, const float *px, const float *py, con
     if (ctx->s[S_DEFER].p != before || ctx->s[S_DEFER].cap != cap_before)
       GV_CUDA(cudaMemsetAsync(d_defer, 0, ctx->s[S_DEFER].cap, ctx->stream));
     fill_fast_args(a, d_defer, fa, &bounded);
+    // bulk copies need 16-byte aligned sources and sizes: plane pointers aligned, every frame
+    // boundary (hence every tile start and size) a multiple of 4 points
+    tma = ctx->use_tma && a.vec_ok;
+    for (int f = 0; f <= nframes && tma; ++f) tma = (foff[f] & 3ull) == 0;
   }
   if (points_on_device) {
     a.tile0 = 0;
-    if (fast) return launch_points_fast(ctx, fa, bounded, 0, ntiles);
+    if (fast) {
+      set_ends_window(ctx, true);
+      const int rc = launch_points_fast(ctx, fa, bounded, tma, 0, ntiles);
+      set_ends_window(ctx, false);
+      return rc;
+    }
     return launch_points(ctx, true, true, a, ntiles, smem);
   }
+  if (fast) set_ends_window(ctx, true);
 
   // host path: pipeline H2D copies, the fused kernel and the label D2H over three streams,
   // a few frames per chunk (~4M points), so PCIe runs in both directions under the compute
@@ -1741,7 +1833,7 @@ static int process_batch_impl(gv_ctx *ctx, const float *px, const float *py, con
     GV_CUDA(cudaStreamWaitEvent(ctx->stream, e_h2d, 0));
     a.tile0 = tile_prefix[f0];
     if (fast) {
-      GV_TRY(launch_points_fast(ctx, fa, bounded, a.tile0, tile_prefix[f1] - tile_prefix[f0]));
+      GV_TRY(launch_points_fast(ctx, fa, bounded, tma, a.tile0, tile_prefix[f1] - tile_prefix[f0]));
     } else {
       GV_TRY(launch_points(ctx, true, true, a, tile_prefix[f1] - tile_prefix[f0], smem));
     }
@@ -1753,6 +1845,7 @@ static int process_batch_impl(gv_ctx *ctx, const float *px, const float *py, con
     }
     f0 = f1;
   }
+  if (fast) set_ends_window(ctx, false);
   GV_CUDA(cudaStreamSynchronize(ctx->d2h_stream));
   GV_CUDA(cudaStreamSynchronize(ctx->stream));
   return GV_OK;
@@ -1854,6 +1947,34 @@ int gv_nccl_world(gv_ctx *ctx, int *rank_out, int *world_out)
   return GV_OK;
 }
 
+#ifdef GV_WITH_NCCL
+// Every rank must hold the same grid geometry and sensor pose (same start cell, hence the same
+// sweep table, span ownership and slab split): a mismatch would merge planes of different maps
+// and, over peer memory, read and write out of bounds.  Checked collectively (min == max of a
+// small descriptor) the first time after the grid or the pose changed.
+static int check_ranks_agree(gv_ctx *ctx)
+{
+  if (ctx->multi_checked) return GV_OK;
+  double h[16] = {(double)ctx->g.nx, (double)ctx->g.ny, ctx->g.res, ctx->g.pos_x, ctx->g.pos_y,
+                  (double)ctx->bin.sx, (double)ctx->bin.sy, (double)ctx->bin.origin_ok};
+  for (int i = 0; i < 8; ++i) h[8 + i] = -h[i];  // max of the negation = -min: one collective
+  double *d = nullptr;
+  GV_TRY(reserve_t(ctx, S_SMALL, 16, &d));
+  GV_CUDA(cudaMemcpyAsync(d, h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
+  GV_NCCL(ncclAllReduce(d, d, 16, ncclDouble, ncclMax, ctx->comm, ctx->stream));
+  double r[16];
+  GV_CUDA(cudaMemcpyAsync(r, d, sizeof(r), cudaMemcpyDeviceToHost, ctx->stream));
+  GV_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < 8; ++i)
+    GV_REQUIRE(r[i] == -r[8 + i], GV_ERR_STATE,
+               "ranks disagree on the grid geometry / sensor pose (field %d: max %.17g, min %.17g): "
+               "every rank must call gv_grid_init* and gv_set_base_transform with the same arguments",
+               i, r[i], -r[8 + i]);
+  ctx->multi_checked = true;
+  return GV_OK;
+}
+#endif
+
 int gv_grid_finalize_multi(gv_ctx *ctx, int32_t k_decay, const double *corners, int nfoot)
 {
   if (!ctx) return GV_ERR_INVALID;
@@ -1862,6 +1983,7 @@ int gv_grid_finalize_multi(gv_ctx *ctx, int32_t k_decay, const double *corners, 
 #ifdef GV_WITH_NCCL
   if (ctx->world == 1 || ctx->comm == nullptr) return finalize_impl(ctx, k_decay, corners, nullptr, nfoot, 0);
   const unsigned world = (unsigned)ctx->world, rank = (unsigned)ctx->rank;
+  GV_TRY(check_ranks_agree(ctx));
   // equal slabs, 4-cell aligned (k_finalize vector width); planes carry kPlanePad slack cells
   size_t slab = (ctx->ncells + world - 1) / world;
   slab = (slab + 3) & ~(size_t)3;

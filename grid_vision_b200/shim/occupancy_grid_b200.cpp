@@ -1,11 +1,17 @@
 // occupancy_grid_b200.cpp — drop-in definitions of class OccupancyGridMap
 // (ref: include/grid_vision/occupancy_grid.hpp:13-40, src/occupancy_grid.cpp:4-196) over the
-// C ABI.  Build it INSTEAD of src/occupancy_grid.cpp.  The header is untouched, so the library
-// context of each map lives in a side table keyed by the object's grid_map_ member.
+// C ABI.  Build it INSTEAD of src/occupancy_grid.cpp.  The header is untouched, so there is no
+// member to hang a library context on, and the object is copied/moved by the node
+// (`occ_grid_ = OccupancyGridMap(...)` into a std::optional, ref: src/grid_vision_node.cpp:35,
+// include/grid_vision/grid_vision_node.hpp:64).  The device twin is therefore found from the
+// GEOMETRY of the grid_map the caller passes (size, resolution, position) and created on first
+// use, never from an object address.
 #include "grid_vision/occupancy_grid.hpp"
 
 #include <cstring>
 #include <map>
+#include <tuple>
+#include <vector>
 
 #include "gv_shim_common.hpp"
 
@@ -14,64 +20,112 @@ namespace
   struct MapState
   {
     gv_ctx *ctx = nullptr;
-    int nx = 0, ny = 0;
+    // log_odds as the device last left it on the host: when the caller's layer still equals it
+    // the device copy is current and the upload is skipped (host edits are detected, not assumed)
+    std::vector<float> shadow;
+    bool shadow_valid = false;
   };
-  std::map<const grid_map::GridMap *, MapState> &states()
+  using GeomKey = std::tuple<int, int, double, double, double>;
+
+  struct Registry
   {
-    static std::map<const grid_map::GridMap *, MapState> s;
-    return s;
+    std::map<GeomKey, MapState> states;
+    ~Registry()
+    {
+      for(auto &kv : states)
+        if(kv.second.ctx)
+          gv_destroy(kv.second.ctx);
+    }
+  };
+  Registry &registry()
+  {
+    static Registry r;
+    return r;
+  }
+
+  // One context per distinct map geometry (the node has exactly one map).  nullptr when no B200
+  // context can be had: the update is then skipped, like the reference's silent error paths.
+  MapState *state_for(const grid_map::GridMap &grid_map)
+  {
+    const auto size = grid_map.getSize();
+    const auto pos = grid_map.getPosition();
+    const double res = grid_map.getResolution();
+    if(size(0) <= 0 || size(1) <= 0 || !(res > 0.0))
+      return nullptr;
+    const GeomKey key(size(0), size(1), res, pos(0), pos(1));
+    auto &states = registry().states;
+    auto it = states.find(key);
+    if(it != states.end())
+      return it->second.ctx ? &it->second : nullptr;
+    MapState st;
+    const char *d = std::getenv("GV_DEVICE");
+    // gv_grid_init takes lengths: size * resolution reproduces the size exactly (setGeometry's
+    // own length_ = size * resolution, grid_map::GridMap::setGeometry)
+    if(gv_create(&st.ctx, d ? std::atoi(d) : 0) != GV_OK
+       || !gv_shim::ok(st.ctx, gv_grid_init(st.ctx, size(0) * res, size(1) * res, res, pos(0), pos(1)),
+                       "gv_grid_init"))
+    {
+      std::fprintf(stderr, "[grid_vision_b200] no B200 context: OccupancyGridMap updates are disabled\n");
+      if(st.ctx)
+        gv_destroy(st.ctx);
+      st.ctx = nullptr;
+    }
+    else
+    {
+      gv_grid_desc desc;
+      gv_grid_get_desc(st.ctx, &desc);
+      if(desc.nx != size(0) || desc.ny != size(1))
+      {
+        std::fprintf(stderr, "[grid_vision_b200] device grid %dx%d != host grid %dx%d\n", desc.nx, desc.ny,
+                     (int)size(0), (int)size(1));
+        gv_destroy(st.ctx);
+        st.ctx = nullptr;
+      }
+    }
+    auto &slot = states[key];
+    slot = std::move(st);
+    return slot.ctx ? &slot : nullptr;
   }
 
   // The grid the node passes is its own public member grid_map_ (ref:
-  // src/grid_vision_node.cpp:145,208,230,235).  Host-authoritative drop-in: the log_odds layer
-  // is uploaded, updated on the GPU, and both layers are written back, so any host-side edit of
-  // the map between calls is honoured exactly like in the reference.
-  template <typename F> void run_update(grid_map::GridMap &grid_map, F &&update)
+  // src/grid_vision_node.cpp:145,208,230,235).  Host-authoritative drop-in: both layers are
+  // written back after every update, and a host-side edit of log_odds between calls is honoured
+  // exactly like in the reference (the layer is re-uploaded whenever it differs from what the
+  // device last wrote).
+  template <typename F> void run_update(grid_map::GridMap &grid_map, F &&update, bool with_occupancy = true)
   {
-    auto it = states().find(&grid_map);
-    if(it == states().end() || !it->second.ctx)
+    MapState *st = state_for(grid_map);
+    if(!st)
       return;
-    gv_ctx *ctx = it->second.ctx;
+    gv_ctx *ctx = st->ctx;
     Eigen::MatrixXf &lo = grid_map["log_odds"];
     Eigen::MatrixXf &oc = grid_map["occupancy"];
-    if(!gv_shim::ok(ctx, gv_grid_upload(ctx, lo.data(), nullptr), "gv_grid_upload"))
+    const size_t n = static_cast<size_t>(grid_map.getSize()(0)) * static_cast<size_t>(grid_map.getSize()(1));
+    const bool current = st->shadow_valid && st->shadow.size() == n
+                         && std::memcmp(st->shadow.data(), lo.data(), n * sizeof(float)) == 0;
+    st->shadow_valid = false;
+    if(!current && !gv_shim::ok(ctx, gv_grid_upload(ctx, lo.data(), nullptr), "gv_grid_upload"))
       return;
     if(!gv_shim::ok(ctx, update(ctx), "gv_grid_update"))
       return;
-    gv_shim::ok(ctx, gv_grid_download(ctx, lo.data(), oc.data()), "gv_grid_download");
+    if(!gv_shim::ok(ctx, gv_grid_download(ctx, lo.data(), with_occupancy ? oc.data() : nullptr), "gv_grid_download"))
+      return;
+    st->shadow.assign(lo.data(), lo.data() + n);
+    st->shadow_valid = true;
   }
 }
 
 OccupancyGridMap::OccupancyGridMap(const std::string &base_link, uint8_t grid_x,
                                    uint8_t grid_y, double resolution)
 {
-  // host-side container exactly as the reference builds it (:8-13) ...
+  // host-side container exactly as the reference builds it (:8-13); the device twin is created
+  // by the first update from this geometry (state_for), so copies and moves of *this are harmless
   grid_map_ = grid_map::GridMap({"log_odds", "occupancy"});
   grid_map_.setFrameId(base_link);
   grid_map_.setGeometry(grid_map::Length(grid_x, grid_y), resolution);
   grid_map_.setPosition(grid_map::Position(grid_x / 3, 0.0));
   grid_map_["log_odds"].setConstant(log_odds_prior_);
   grid_map_["occupancy"].setConstant(init_probability_);
-  // ... and its device twin with the same geometry
-  MapState st;
-  const char *d = std::getenv("GV_DEVICE");
-  if(gv_create(&st.ctx, d ? std::atoi(d) : 0) == GV_OK
-     && gv_shim::ok(st.ctx, gv_grid_init_reference(st.ctx, grid_x, grid_y, resolution),
-                    "gv_grid_init_reference"))
-  {
-    gv_grid_desc desc;
-    gv_grid_get_desc(st.ctx, &desc);
-    st.nx = desc.nx;
-    st.ny = desc.ny;
-  }
-  else
-  {
-    std::fprintf(stderr, "[grid_vision_b200] no B200 context: OccupancyGridMap updates are disabled\n");
-    if(st.ctx)
-      gv_destroy(st.ctx);
-    st.ctx = nullptr;
-  }
-  states()[&grid_map_] = st;
 }
 
 // ref: src/occupancy_grid.cpp:16-31
@@ -138,10 +192,6 @@ OccupancyGridMap::computeBoundingBox3D(const geometry_msgs::msg::Point &base_cen
 void OccupancyGridMap::updateGridCellsFast(
   grid_map::GridMap &grid_map, const std::array<geometry_msgs::msg::Point, 4> &bbox_corners)
 {
-  auto it = states().find(&grid_map);
-  if(it == states().end() || !it->second.ctx)
-    return;
-  gv_ctx *ctx = it->second.ctx;
   double c[8];
   for(int i = 0; i < 4; ++i)
   {
@@ -149,10 +199,7 @@ void OccupancyGridMap::updateGridCellsFast(
     c[2 * i + 1] = bbox_corners[i].y;
   }
   // one footprint, no decay: finalize with k_decay = 0 leaves every other cell's log-odds as is
-  Eigen::MatrixXf &lo = grid_map["log_odds"];
-  if(gv_shim::ok(ctx, gv_grid_upload(ctx, lo.data(), nullptr), "gv_grid_upload")
-     && gv_shim::ok(ctx, gv_grid_finalize(ctx, 0, c, 1), "gv_grid_finalize"))
-    gv_shim::ok(ctx, gv_grid_download(ctx, lo.data(), nullptr), "gv_grid_download");
+  run_update(grid_map, [&](gv_ctx *ctx) { return gv_grid_finalize(ctx, 0, c, 1); }, false);
 }
 
 // ref: src/occupancy_grid.cpp:185-196

@@ -17,7 +17,11 @@
  *    synchronous on return (drop-in for the reference's blocking calls);
  *    functions ending in _dev take DEVICE pointers for the bulk arrays (points, labels and
  *    gv_box records; per-frame offset tables stay host arrays) and are asynchronous on the
- *    context stream (gv_stream / gv_set_stream).
+ *    context stream (gv_stream / gv_set_stream).  A fresh context owns a private NON-BLOCKING
+ *    stream, which is not ordered against any other stream (not even the legacy default
+ *    stream): a caller whose device buffers are produced or consumed on another stream must
+ *    either hand that stream over with gv_set_stream, or order the two with events /
+ *    gv_synchronize.  The Python binding binds torch's current stream automatically.
  *  - point clouds are SoA float planes (x[], y[], z[]); the reference's
  *    pcl::PointCloud<pcl::PointXYZI> 32-byte AoS records are accepted by the *_aos32 entry
  *    points and de-interleaved on the device.
@@ -267,7 +271,9 @@ GV_API int gv_grid_to_occupancy(gv_ctx *ctx, int8_t *data_out);
 GV_API int gv_nccl_unique_id(void *id128_out);
 GV_API int gv_nccl_init(gv_ctx *ctx, const void *id128, int rank, int world);
 GV_API int gv_nccl_world(gv_ctx *ctx, int *rank_out, int *world_out);
-/* Collective finalize: all ranks' binned beams are summed (exact int sums over NVLink), the
+/* Collective finalize.  Every rank must have initialised the SAME grid geometry and set the SAME
+ * base transform (verified collectively the first time after either changed: GV_ERR_STATE on a
+ * mismatch).  All ranks' binned beams are summed (exact int sums over NVLink), the
  * de-duplicated raycast is split across ranks, partial miss planes are reduce-scattered,
  * every rank finalises its slab of the grid and the slabs are all-gathered, so each rank
  * ends with the identical full grid.  Bit-identical to a single-context run. */

@@ -5,6 +5,7 @@
 #include "grid_vision/occupancy_grid.hpp"
 
 #include <cstring>
+#include <optional>
 
 static_assert(sizeof(BoundingBox) == 40, "BoundingBox layout (object_detection.hpp:27-32)");
 
@@ -85,6 +86,16 @@ int ref_compute_bbox_pose_empty()
 // OccupancyGridMap (src/occupancy_grid.cpp:4-196)
 void *ref_grid_new(uint8_t gx, uint8_t gy, double res) { return new OccupancyGridMap("base", gx, gy, res); }
 void ref_grid_free(void *g) { delete static_cast<OccupancyGridMap *>(g); }
+
+// The node's own construction pattern (src/grid_vision_node.cpp:35 with the member declared at
+// include/grid_vision/grid_vision_node.hpp:64): a temporary assigned into a std::optional, i.e.
+// the object every later updateMap sees is a moved copy, not the one the constructor ran on.
+void *ref_grid_new_like_node(uint8_t gx, uint8_t gy, double res)
+{
+  std::optional<OccupancyGridMap> occ_grid_;
+  occ_grid_ = OccupancyGridMap("base", gx, gy, res);
+  return new OccupancyGridMap(std::move(*occ_grid_));
+}
 
 void ref_grid_desc(void *g, int *nx, int *ny, double *len, double *pos, double *res)
 {

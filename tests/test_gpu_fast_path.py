@@ -172,28 +172,39 @@ def test_fast_path_index_adversarial(ctx, geom):
 
 
 # ----------------------------------------------------------------- template variants
-@pytest.mark.parametrize("unroll", ["1", "2", "4"])
-def test_fast_path_unroll_variants_ragged(unroll):
-    """GV_FAST_U = 1 / 2 / 4 points per thread per iteration on ragged frames (every tail length)."""
-    os.environ["GV_FAST_U"] = unroll
+VARIANTS = [{"GV_FAST_U": "1"}, {"GV_FAST_U": "4"}, {"GV_FAST_AGG": "0"}, {"GV_FAST_AGG": "2"},
+            {"GV_FAST_AGG": "2", "GV_FAST_U": "1"}, {"GV_NO_TMA": "1"}, {"GV_NO_TMA": "1", "GV_FAST_AGG": "0"},
+            {"GV_NO_TMA": "1", "GV_FAST_AGG": "2", "GV_FAST_U": "4"}, {"GV_L2_PERSIST": "0"}]
+
+
+@pytest.mark.parametrize("env", VARIANTS, ids=lambda e: ",".join(f"{k[3:]}={v}" for k, v in e.items()))
+def test_fast_path_kernel_variants(env):
+    """Every instantiation family (points per thread, RED aggregation mode, TMA-fed persistent kernel
+    vs per-tile LDG kernel, L2 window) on three frame layouts: arbitrary ragged sizes (LDG kernel:
+    bulk copies need 4-point alignment), ragged sizes that are multiples of 4 (TMA kernel, partial
+    last rows), and one-point / empty frames."""
+    os.environ.update(env)
     try:
         c = gv.Context(0)
     finally:
-        del os.environ["GV_FAST_U"]
+        for k in env:
+            del os.environ[k]
     try:
         wl = small(synth.C3, rings=16, azimuth=1024, grid_nx=1024, grid_ny=1024)
         P = wl.points_per_frame
         nframes = 9
         full = scan(wl, frames=nframes)
         rng = np.random.default_rng(5)
-        sizes = rng.integers(1, P + 1, nframes)
-        sizes[1], sizes[2], sizes[3] = 0, 1, 257
-        keep = np.concatenate([np.arange(f * P, f * P + sizes[f]) for f in range(nframes)])
-        xyz = np.ascontiguousarray(full[:, keep])
-        fo = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+        Tc, Tb = synth.camera_extrinsics(1)[0], synth.T_base_lidar()
         per_frame = [synth.make_boxes(wl, frame=f, n=int(3 + 11 * f) % 65) for f in range(nframes)]
-        check_batch(c, wl, xyz, fo, per_frame, synth.camera_extrinsics(1)[0], synth.T_base_lidar(), r_max=wl.r_max)
-        check_batch(c, wl, xyz, fo, per_frame, synth.camera_extrinsics(1)[0], synth.T_base_lidar())
+        for align in (1, 4):
+            sizes = rng.integers(1, P // align + 1, nframes) * align
+            sizes[1], sizes[2], sizes[3] = 0, align, 256 + align
+            keep = np.concatenate([np.arange(f * P, f * P + sizes[f]) for f in range(nframes)])
+            xyz = np.ascontiguousarray(full[:, keep])
+            fo = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+            check_batch(c, wl, xyz, fo, per_frame, Tc, Tb, r_max=wl.r_max)
+            check_batch(c, wl, xyz, fo, per_frame, Tc, Tb)  # no range cap: unbounded index words
     finally:
         c.close()
 

@@ -71,9 +71,12 @@ def test_compute_bbox_pose_empty_convention(libs):
     assert ref.ref_compute_bbox_pose_empty() == shim.ref_compute_bbox_pose_empty() == 0
 
 
-def test_occupancy_grid_map_drop_in(libs):
+@pytest.mark.parametrize("like_node", [False, True], ids=["heap", "optional-move-like-the-node"])
+def test_occupancy_grid_map_drop_in(libs, like_node):
+    """like_node: the map is built the way src/grid_vision_node.cpp:35 builds it (a temporary moved
+    into a std::optional), so the object that is updated is not the one the constructor ran on."""
     ref, shim = libs
-    a, b = RefGrid(ref, 50, 20, 0.1), RefGrid(shim, 50, 20, 0.1)
+    a, b = RefGrid(ref, 50, 20, 0.1, like_node), RefGrid(shim, 50, 20, 0.1, like_node)
     assert (a.nx, a.ny, a.len, a.pos) == (b.nx, b.ny, b.len, b.pos)
     rng = np.random.default_rng(4)
     lo0 = rng.uniform(-2.5, 4.0, a.nx * a.ny).astype(f32)
@@ -97,6 +100,11 @@ def test_occupancy_grid_map_drop_in(libs):
             lab = rng.integers(0, 11, n).astype(np.int32)
             for lib, g in ((ref, a), (shim, b)):
                 lib.ref_update_map_points(g.h, p(xy), p(lab), C.c_int(n))
+        if k == 7:  # another host-side edit mid-sequence (the shim must notice and re-upload)
+            lo1 = rng.uniform(-2.5, 4.0, a.nx * a.ny).astype(f32)
+            a.write(lo1)
+            b.write(lo1)
+            continue
         la, oa = a.read()
         lb, ob = b.read()
         assert np.array_equal(la.view(np.uint32), lb.view(np.uint32)), f"log_odds, step {k}"

@@ -129,9 +129,11 @@ def test_compute_bbox_pose_empty_cloud_convention(ref):
 
 
 class RefGrid:
-    def __init__(self, ref, gx, gy, res):
+    def __init__(self, ref, gx, gy, res, like_node=False):
         self.ref = ref
-        self.h = C.c_void_p(ref.ref_grid_new(C.c_uint8(gx), C.c_uint8(gy), C.c_double(res)))
+        new = ref.ref_grid_new_like_node if like_node else ref.ref_grid_new
+        new.restype = C.c_void_p
+        self.h = C.c_void_p(new(C.c_uint8(gx), C.c_uint8(gy), C.c_double(res)))
         nx, ny, r = C.c_int(), C.c_int(), C.c_double()
         ln, ps = (C.c_double * 2)(), (C.c_double * 2)()
         ref.ref_grid_desc(self.h, C.byref(nx), C.byref(ny), ln, ps, C.byref(r))
