@@ -17,8 +17,14 @@ calls (gv_process_batch + gv_grid_finalize[_multi] + gv_grid_download) with pinn
 buffers, H2D/D2H inside the timed region.
 
 --impl reference times the CPU oracle port (oracle/, the restatement of the reference's CPU
-path; the reference itself cannot be built here: no ROS 2 / PCL / Eigen / grid_map) on all
-host threads, on a bounded sample of the same workload.
+path, pinned bit for bit to the reference's own two hot-path sources compiled into oracle/_ref;
+the reference's real build needs ROS 2 / PCL / Eigen / grid_map and cannot run here) on all host
+threads, on a bounded sample of the same workload.
+
+Every line carries `grid_crc`: CRC-32 of the log-odds layer after CRC_STEPS steps from a reset
+grid.  The batch-sum semantics make it independent of the GPU count, so the N = 1, 2, 4, 8 lines
+of a scaling run must show the same value; at N = 1 `parity_sample` repeats that on a bounded
+number of frames against the CPU oracle.
 """
 from __future__ import annotations
 
@@ -29,6 +35,7 @@ import subprocess
 import sys
 import threading
 import time
+import zlib
 
 import numpy as np
 
@@ -38,8 +45,10 @@ if ROOT not in sys.path:
 
 METRIC = "points/sec through project+bbox-fuse+grid-update"
 UNIT = "points/s"
+DTYPE = "f32 transform / f64 projection+indices / i32 counts"
 B_PT = 14   # algorithmic bytes per point: read x,y,z (12) + write int16 label (2)   SURVEY §8.d
 B_CELL = 12  # algorithmic bytes per grid cell: read log_odds, write log_odds + occupancy
+CRC_STEPS = 2  # steps from a reset grid behind `grid_crc`
 
 
 def measured_peak_gbs():
@@ -61,7 +70,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -110,9 +119,12 @@ class CpuOracle:
         from oracle import gv_oracle as orc
         self.wl, self.threads = wl, max(1, threads)
         self.grids = [orc.Grid.from_cells(wl.grid_nx, wl.grid_ny, wl.resolution) for _ in range(self.threads)]
+        self.last_fixed = 0.0
 
     def run(self, xyz, boxes_per_frame):
-        """One pass over the frames in xyz ([3, F*P] numpy).  Returns seconds."""
+        """One pass over the frames in xyz ([3, F*P] numpy).  Returns seconds (whole pass); the
+        part that does not scale with the frame count (merge of the private grids + finalise) is
+        left in self.last_fixed."""
         from concurrent.futures import ThreadPoolExecutor
 
         from grid_vision_b200 import synth
@@ -133,20 +145,30 @@ class CpuOracle:
                 lab, _, _, _ = orc.project_label(K, wl.image_w, wl.image_h, cx, cy, cz, boxes_per_frame[f])
                 g.accumulate(Tb, fx[0], fx[1], fx[2], lab, r_max=wl.r_max, want_cells=False)
 
+        def merge(t):  # thread t sums its slab of every private plane into grid 0
+            n = wl.cells
+            a, b = t * n // threads, (t + 1) * n // threads
+            for g in grids[1:threads]:
+                grids[0].hit[a:b] += g.hit[a:b]
+                grids[0].miss[a:b] += g.miss[a:b]
+                g.hit[a:b] = 0
+                g.miss[a:b] = 0
+
         t0 = time.perf_counter()
         with ThreadPoolExecutor(threads) as ex:
             list(ex.map(work, range(threads)))
-        for g in grids[1:threads]:
-            grids[0].hit += g.hit
-            grids[0].miss += g.miss
-            g.hit[:] = 0
-            g.miss[:] = 0
+            t1 = time.perf_counter()
+            list(ex.map(merge, range(threads)))
         grids[0].finalize(F)
-        return time.perf_counter() - t0
+        t2 = time.perf_counter()
+        self.last_fixed = t2 - t1
+        return t2 - t0
 
 
-def cpu_oracle_run(wl, xyz, boxes_per_frame, threads):
-    return CpuOracle(wl, threads).run(xyz, boxes_per_frame)
+def cpu_sample_frames(cores):
+    """Frames per CPU step: enough that the merge + finalise tail (independent of the frame count)
+    stays a few per cent of the step, as it is on the real 4096-frame job."""
+    return max(32, min(8 * cores, 256))
 
 
 def cpu_sample(wl, frames):
@@ -156,27 +178,113 @@ def cpu_sample(wl, frames):
     return xyz, boxes
 
 
+def cpu_variants_single_thread(wl, xyz, boxes, frames=3):
+    """BASELINE.md section 2 variants 1 and 2, one thread, `frames` frames each:
+    1 reference-shaped: 32-byte AoS points, per-box push_back clouds (the reference's
+      extractCloudPerBBox), then decay / clamp / sigmoid passes over the grid every frame;
+    2 oracle SoA: labels only, integer planes, one finalise at the end."""
+    from grid_vision_b200 import synth
+    from oracle import gv_oracle as orc
+    P = wl.points_per_frame
+    Tc, Tb, K = synth.camera_extrinsics(1)[0], synth.T_base_lidar(), wl.K()
+    g = orc.Grid.from_cells(wl.grid_nx, wl.grid_ny, wl.resolution)
+    t1 = 0.0
+    for f in range(frames):
+        fx = xyz[:, f * P:(f + 1) * P]
+        t0 = time.perf_counter()
+        cx, cy, cz = orc.transform_points(Tc, fx[0], fx[1], fx[2])
+        t1 += time.perf_counter() - t0
+        aos = synth.points_aos32(np.stack([cx, cy, cz]))  # container conversion: not timed
+        t0 = time.perf_counter()
+        orc.extract_cloud_per_bbox_aos(aos, K, boxes[f], wl.image_w, wl.image_h)
+        g.accumulate(Tb, fx[0], fx[1], fx[2], None, r_max=wl.r_max, want_cells=False)
+        g.finalize(1)
+        t1 += time.perf_counter() - t0
+    g2 = orc.Grid.from_cells(wl.grid_nx, wl.grid_ny, wl.resolution)
+    t0 = time.perf_counter()
+    for f in range(frames):
+        fx = xyz[:, f * P:(f + 1) * P]
+        cx, cy, cz = orc.transform_points(Tc, fx[0], fx[1], fx[2])
+        lab, _, _, _ = orc.project_label(K, wl.image_w, wl.image_h, cx, cy, cz, boxes[f])
+        g2.accumulate(Tb, fx[0], fx[1], fx[2], lab, r_max=wl.r_max, want_cells=False)
+    g2.finalize(frames)
+    t2 = time.perf_counter() - t0
+    n = frames * P
+    return {"reference_shaped_aos_1thread": {"value": n / t1, "unit": UNIT, "cores": 1, "frames": frames},
+            "oracle_soa_1thread": {"value": n / t2, "unit": UNIT, "cores": 1, "frames": frames}}
+
+
+def c1_reference_vs_shim(reps=5):
+    """BASELINE configs[0] is literally "reference CPU path": time the reference's OWN compiled
+    extractCloudPerBBox + updateMap(LShapePose) (oracle/_ref/libgv_ref.so = its two hot-path
+    sources, unmodified) on one C1 frame, and the drop-in shim (libgv_shim.so = the same C++
+    signatures over the C ABI and the CUDA kernels) through the same harness calls."""
+    import ctypes as C
+
+    from grid_vision_b200 import synth
+    from oracle import gv_oracle as orc
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "libgv_ref.so")
+    shim_so = os.path.join(ROOT, "oracle", "_ref", "libgv_shim.so")
+    if not (os.path.exists(ref_so) and os.path.exists(shim_so)):
+        return None
+    wl = synth.C1
+    xyz = synth.make_scans(wl, frames=1, device="cpu").numpy()
+    cam = [np.ascontiguousarray(a) for a in orc.transform_points(synth.camera_extrinsics(1)[0], *xyz)]
+    boxes = np.ascontiguousarray(synth.make_boxes(wl))
+    K = np.ascontiguousarray(wl.K())
+    poses = np.ascontiguousarray(synth.make_footprints(wl.scaled(pos_x=6.0), n=20))
+    labels = np.empty(wl.points, np.int16)
+    out = {"workload": f"C1 frame: {wl.points} camera-frame points, {len(boxes)} boxes, 416x416; "
+                       "OccupancyGridMap(20, 20, 0.1) = 200x200 cells, 20 object poses",
+           "calls": "cloud_detections::extractCloudPerBBox + OccupancyGridMap::updateMap(grid, poses)"}
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    for name, path in (("reference_ms", ref_so), ("shim_ms", shim_so)):
+        lib = C.CDLL(path)
+        lib.ref_grid_new_like_node.restype = C.c_void_p
+        lib.ref_grid_free.argtypes = [C.c_void_p]
+        lib.ref_update_map_poses.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        g = C.c_void_p(lib.ref_grid_new_like_node(C.c_uint8(20), C.c_uint8(20), C.c_double(0.1)))
+
+        def once():
+            lib.ref_extract_cloud_per_bbox(p(cam[0]), p(cam[1]), p(cam[2]), C.c_size_t(wl.points), p(K),
+                                           p(boxes), C.c_int(len(boxes)), C.c_int(416), C.c_int(416), p(labels))
+            lib.ref_update_map_poses(g, p(poses), C.c_int(len(poses)))
+        once()
+        once()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            once()
+        out[name] = 1e3 * (time.perf_counter() - t0) / reps
+        lib.ref_grid_free(g)
+    out["speedup"] = out["reference_ms"] / out["shim_ms"]
+    return out
+
+
 def run_reference_arm(args, wl):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    frames = max(2, min(2 * cores, 64))
+    frames = cpu_sample_frames(cores)
     xyz, boxes = cpu_sample(wl, frames)
     pts = xyz.shape[1]
     cpu = CpuOracle(wl, cores)
     for _ in range(max(1, min(args.warmup, 1))):
         cpu.run(xyz, boxes)
-    ts = [cpu.run(xyz, boxes) for _ in range(args.steps)]
+    ts, fixed = [], []
+    for _ in range(args.steps):
+        ts.append(cpu.run(xyz, boxes))
+        fixed.append(cpu.last_fixed)
     t = float(np.mean(ts))
     v = pts / t
-    sample = f"{frames} frames ({pts} points) of the workload per step, frame-parallel on {cores} threads"
+    sample = (f"{frames} frames ({pts} points) of the workload per step, frame-parallel on {cores} threads; "
+              f"merge+finalise tail {100 * float(np.mean(fixed)) / t:.1f} % of the step")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32 transform / f64 projection+indices / i32 counts", "data": "synthetic",
-        "config": workload_config(wl, wl.frames, args.gpus, sample=sample),
+        "dtype": DTYPE, "data": "synthetic",
+        "config": workload_config(wl, wl.frames, args.gpus),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -204,27 +312,59 @@ def time_loop(torch, fn, iters, warm=3):
     return a.elapsed_time(b) / iters
 
 
-def other_configs(torch, gv, synth, ctx, dev):
-    """The remaining BASELINE.json configs, resident inputs, CUDA-event timed (N = 1 only).
-    Each entry: milliseconds per pass and points/s; parity for every one of them is in tests/."""
-    out = {}
-    # C1 / C2: one scan -> fuse + bin + raycast + finalise (latency-bound: a few launches)
-    for wl in (synth.C1, synth.C2):
-        xyz = synth.make_scans(wl, frames=1, device=dev)
-        boxes = synth.make_boxes(wl)
-        d_boxes = torch.from_numpy(boxes.view(np.uint8).copy()).to(dev)
-        lab = torch.empty(wl.points, dtype=torch.int16, device=dev)
-        fo = np.array([0, wl.points], np.uint64)
-        bo = np.array([0, len(boxes)], np.int32)
-        ctx.grid_init_cells(wl.grid_nx, wl.grid_ny, wl.resolution)
-        ctx.set_base_transform(synth.T_base_lidar())
-        prm = gv.accum_params(r_max=wl.r_max)
+def timed_batch(torch, gv, synth, ctx, dev, wl, frames, iters, adversarial=False):
+    """Resident batch of `frames` scans of wl: ms per pass split into the fused point kernel and
+    raycast + finalise, plus the raycast counters per pass."""
+    P = wl.points_per_frame
+    xyz = synth.make_scans(wl, frames=frames, device=dev, adversarial=adversarial)
+    boxes = np.concatenate([synth.make_boxes(wl, frame=f) for f in range(frames)])
+    d_boxes = torch.from_numpy(boxes.view(np.uint8).copy()).to(dev)
+    lab = torch.empty(frames * P, dtype=torch.int16, device=dev)
+    fo = np.arange(frames + 1, dtype=np.uint64) * np.uint64(P)
+    bo = (np.arange(frames + 1) * wl.boxes_per_camera).astype(np.int32)
+    ctx.grid_init_cells(wl.grid_nx, wl.grid_ny, wl.resolution)
+    ctx.set_base_transform(synth.T_base_lidar())
+    prm = gv.accum_params(r_max=wl.r_max)
 
-        def one():
-            ctx.process_batch(xyz[0], xyz[1], xyz[2], fo, d_boxes, bo, prm, lab)
-            ctx.grid_finalize(1)
-        ms = time_loop(torch, one, 50)
-        out[f"C{wl.config_id}"] = {"workload": wl.name, "ms": ms, "points_per_s": wl.points / (ms * 1e-3)}
+    def one(ev=None):
+        if ev:
+            ev[0].record()
+        ctx.process_batch(xyz[0], xyz[1], xyz[2], fo, d_boxes, bo, prm, lab)
+        if ev:
+            ev[1].record()
+        ctx.grid_finalize(frames)
+        if ev:
+            ev[2].record()
+    for _ in range(3):
+        one()
+    torch.cuda.synchronize()
+    st0 = ctx.stats()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(iters)]
+    for k in range(iters):
+        one(evs[k])
+    torch.cuda.synchronize()
+    st1 = ctx.stats()
+    ms_pts = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
+    ms_ray = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
+    ms = ms_pts + ms_ray
+    per = lambda k: (st1[k] - st0[k]) / iters
+    return {"workload": wl.name + (" (adversarial ranges r ~ U(2, sensor_range))" if adversarial else ""),
+            "frames": frames, "points": frames * P, "ms": ms, "ms_points_kernel": ms_pts,
+            "ms_raycast_finalize": ms_ray, "points_per_s": frames * P / (ms * 1e-3),
+            "cells_logical_per_s": per("cells_logical") / (ms * 1e-3),
+            "raycast_reds_per_s": per("cells_physical") / (ms_ray * 1e-3),
+            "distinct_end_cells": per("distinct_ends"), "grid_cells": wl.cells}
+
+
+def other_configs(torch, gv, synth, ctx, dev):
+    """The remaining BASELINE.json configs and the hard-input variant of C3, resident inputs,
+    CUDA-event timed (N = 1 only).  Parity for every one of them is in tests/."""
+    out = {}
+    # C1 / C2: one scan -> fuse + bin + raycast + finalise (the node's 20 Hz call pattern)
+    for wl in (synth.C1, synth.C2):
+        r = timed_batch(torch, gv, synth, ctx, dev, wl, 1, 50)
+        out[f"C{wl.config_id}"] = {k: r[k] for k in ("workload", "ms", "ms_points_kernel", "ms_raycast_finalize",
+                                                      "points_per_s")}
     # C4: 6-camera rig, 300 boxes, 1M-point cloud (fusion only, one label plane per camera)
     wl = synth.C4
     xyz = synth.make_scans(wl, frames=1, device=dev)
@@ -239,44 +379,75 @@ def other_configs(torch, gv, synth, ctx, dev):
     out["C4"] = {"workload": wl.name, "ms": ms, "points_per_s": wl.points / (ms * 1e-3),
                  "camera_projections_per_s": 6 * wl.points / (ms * 1e-3)}
     ctx.set_cameras(wl.K().reshape(1, 9), [[wl.image_w, wl.image_h]], synth.camera_extrinsics(1))
+    del xyz, lab6
     # C5: 8192x8192 grid @0.05 m, 16.7M points per batch, 120 m rays
-    wl = synth.C5
-    xyz = synth.make_scans(wl, device=dev)
-    boxes = np.concatenate([synth.make_boxes(wl, frame=f) for f in range(wl.frames)])
-    d_boxes = torch.from_numpy(boxes.view(np.uint8).copy()).to(dev)
-    lab = torch.empty(wl.points, dtype=torch.int16, device=dev)
-    fo = np.arange(wl.frames + 1, dtype=np.uint64) * np.uint64(wl.points_per_frame)
-    bo = (np.arange(wl.frames + 1) * wl.boxes_per_camera).astype(np.int32)
-    ctx.grid_init_cells(wl.grid_nx, wl.grid_ny, wl.resolution)
-    ctx.set_base_transform(synth.T_base_lidar())
-    prm = gv.accum_params(r_max=wl.r_max)
-    st0 = ctx.stats()
-
-    def one5():
-        ctx.process_batch(xyz[0], xyz[1], xyz[2], fo, d_boxes, bo, prm, lab)
-        ctx.grid_finalize(wl.frames)
-    ms = time_loop(torch, one5, 10)
-    st1 = ctx.stats()
-    passes = 13
-    out["C5"] = {"workload": wl.name, "ms": ms, "points_per_s": wl.points / (ms * 1e-3),
-                 "cells_logical_per_s": (st1["cells_logical"] - st0["cells_logical"]) / passes / (ms * 1e-3),
-                 "grid_cells": wl.cells}
+    out["C5"] = timed_batch(torch, gv, synth, ctx, dev, synth.C5, synth.C5.frames, 10)
+    # C3 geometry with adversarial ranges: end cells do not repeat from frame to frame, so the
+    # raycast's de-duplication has little to bite on
+    out["C3_adversarial"] = timed_batch(torch, gv, synth, ctx, dev, synth.C3, 256, 5, adversarial=True)
+    # "next" rows N1 / N2 on one C2 scan (host-pointer entry points: copies included)
+    wl = synth.C2
+    h = synth.make_scans(wl, frames=1, device="cpu").numpy()
+    ctx.set_cameras(wl.K().reshape(1, 9), [[wl.image_w, wl.image_h]], synth.camera_extrinsics(1))
+    for n_hyp in (256, 1024):
+        t0 = time.perf_counter()
+        for _ in range(3):
+            ctx.segment_ground(h[0], h[1], h[2], n_hyp=n_hyp)
+        out[f"N1_segment_ground_{n_hyp}hyp"] = {"ms": 1e3 * (time.perf_counter() - t0) / 3, "points": wl.points}
+    labels, _, _ = ctx.fuse(h[0], h[1], h[2], synth.make_boxes(wl), want_pix=False, want_uv=False)
+    cam = ctx.transform_points(0, h[0], h[1], h[2])
+    t0 = time.perf_counter()
+    for _ in range(3):
+        ctx.bbox_pose(cam[0], cam[1], cam[2], labels[0], wl.boxes_per_camera)
+    out["N2_bbox_pose"] = {"ms": 1e3 * (time.perf_counter() - t0) / 3, "points": wl.points,
+                           "labelled_points": int((labels[0] >= 0).sum())}
     return out
 
 
-def workload_config(wl, frames, gpus, **extra):
-    c = {"workload": f"C3 batched replay: {frames} synthetic 64-beam scans x {wl.points_per_frame} pts, "
-                     f"{wl.boxes_per_camera} boxes/scan, 416x416 camera, {wl.grid_nx}x{wl.grid_ny} grid "
-                     f"@{wl.resolution} m, r_max {wl.r_max} m, batch_sum semantics",
-         "frames": frames, "points": frames * wl.points_per_frame, "cells": wl.cells,
-         "sharding": f"frames split contiguously over {gpus} rank(s); NCCL int merge in finalize",
-         "l2": "inputs larger than L2: each rank streams its resident point planes "
-               "(>= 800 MB at 8 ranks) once per step",
-         "why_this_config": "BASELINE.json quotes the metric (>= 1e10 points/s on 8xB200, reported at 1/2/4/8 "
-                            "GPUs) on configs[2], the batched replay, and it fits one GPU (6.4 GB of points); "
-                            "configs[1] (one 262k-point scan, latency-bound) is measured under other_configs.C2"}
-    c.update(extra)
-    return c
+def workload_config(wl, frames, gpus):
+    """Identical in both arms (the driver compares the two dicts); what differs between the arms
+    (sample size, merge implementation) lives in their own top-level keys."""
+    return {"workload": f"C3 batched replay: {frames} synthetic 64-beam scans x {wl.points_per_frame} pts, "
+                        f"{wl.boxes_per_camera} boxes/scan, 416x416 camera, {wl.grid_nx}x{wl.grid_ny} grid "
+                        f"@{wl.resolution} m, r_max {wl.r_max} m, batch_sum semantics",
+            "frames": frames, "points": frames * wl.points_per_frame, "cells": wl.cells,
+            "sharding": f"frames split contiguously over {gpus} rank(s); per-rank integer planes merged exactly "
+                        "inside the finalise call",
+            "l2": "inputs larger than L2: each rank streams its resident point planes "
+                  "(>= 800 MB at 8 ranks) once per step",
+            "why_this_config": "BASELINE.json quotes the metric (>= 1e10 points/s on 8xB200, reported at 1/2/4/8 "
+                               "GPUs) on configs[2], the batched replay, and it fits one GPU (6.4 GB of points); "
+                               "configs[1] (one 262k-point scan, latency-bound) is measured under other_configs.C2"}
+
+
+def grid_crc(ctx):
+    lo, _ = ctx.grid_download()
+    return zlib.crc32(np.ascontiguousarray(lo).view(np.uint8).tobytes()) & 0xffffffff
+
+
+def parity_sample(torch, gv, synth, ctx, dev, wl, frames=16):
+    """N = 1: `frames` full-size frames of the workload through the GPU path from a reset grid and
+    through the CPU oracle; CRCs of the log-odds layers and label equality."""
+    from oracle import gv_oracle as orc
+    P = wl.points_per_frame
+    xyz = synth.make_scans(wl, frames=frames, device="cpu", chunk=2).numpy()
+    per = [synth.make_boxes(wl, frame=f) for f in range(frames)]
+    fo = np.arange(frames + 1, dtype=np.uint64) * np.uint64(P)
+    bo = (np.arange(frames + 1) * wl.boxes_per_camera).astype(np.int32)
+    ctx.grid_reset()
+    labels = ctx.process_batch(xyz[0], xyz[1], xyz[2], fo, np.concatenate(per), bo, gv.accum_params(r_max=wl.r_max))
+    ctx.grid_finalize(frames)
+    crc_gpu = grid_crc(ctx)
+    cores = os.cpu_count() or 1
+    cpu = CpuOracle(wl, min(cores, frames))
+    Tc, K = synth.camera_extrinsics(1)[0], wl.K()
+    cpu.run(xyz, per)
+    lo = cpu.grids[0].log_odds
+    crc_cpu = zlib.crc32(np.ascontiguousarray(lo).view(np.uint8).tobytes()) & 0xffffffff
+    cx, cy, cz = orc.transform_points(Tc, xyz[0, :P], xyz[1, :P], xyz[2, :P])
+    elab, _, _, _ = orc.project_label(K, wl.image_w, wl.image_h, cx, cy, cz, per[0])
+    return {"frames": frames, "grid_crc": f"{crc_gpu:08x}", "grid_crc_oracle": f"{crc_cpu:08x}",
+            "grids_equal": crc_gpu == crc_cpu, "labels_frame0_equal": bool(np.array_equal(labels[:P], elab))}
 
 
 # --------------------------------------------------------------------------- our arm
@@ -434,43 +605,79 @@ def main():
                "api": "gv_process_batch + gv_grid_finalize" + ("_multi" if multi else "") +
                       " + gv_grid_download, pinned host buffers"}
 
+    # ---- result checksum: CRC_STEPS steps from a reset grid; identical at every N by construction
+    ctx.grid_reset()
+    for _ in range(CRC_STEPS):
+        step_resident()
+    barrier()
+    crc = grid_crc(ctx)
+    if world > 1:  # every rank holds the full merged grid: they must all agree
+        t = torch.tensor([crc], dtype=torch.int64, device=dev)
+        tmin, tmax = t.clone(), t.clone()
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ranks_agree = bool(tmin.item() == tmax.item())
+    else:
+        ranks_agree = True
+
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         pts_bytes = n_local * B_PT
         achieved = pts_bytes / (ms_points * 1e-3) / 1e9
         dst = st1["distinct_ends"] - st0["distinct_ends"]
+        phys = (st1["cells_physical"] - st0["cells_physical"]) / args.steps
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32 transform / f64 projection+indices / i32 counts", "data": "synthetic",
-            "config": workload_config(wl, F, world, merge=merge),
+            "dtype": DTYPE, "data": "synthetic",
+            "config": workload_config(wl, F, world), "merge": merge,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "gv::k_points<true,true> (fused transform+project+label+bin)",
+            "grid_crc": f"{crc:08x}", "grid_crc_steps": CRC_STEPS, "grid_crc_ranks_agree": ranks_agree,
+            "roofline": {"bound": "hbm", "kernel": "gv::k_points_tma (fused transform+project+label+bin, TMA-fed)",
                          "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None,
                          "algorithmic_bytes_per_launch": pts_bytes, "ms_per_launch": ms_points},
             "phases_ms": {"fuse_bin": ms_points, "raycast_merge_finalize": ms_final},
             "cells_per_s": {"logical": (st1["cells_logical"] - st0["cells_logical"]) / args.steps / (ms_step * 1e-3),
-                            "physical": (st1["cells_physical"] - st0["cells_physical"]) / args.steps / (ms_step * 1e-3),
+                            "physical": phys / (ms_step * 1e-3),
                             "distinct_ends_per_step": dst / args.steps},
         }
         tr = measured_traffic()
         if tr:
             out["roofline"]["traffic"] = tr["dram_bytes_per_point"] * n_local
             out["roofline"]["traffic_source"] = tr["source"]
+        if world == 1:
+            # K2 / K3 against the measured atomic ceilings of this device
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "scripts"))
+                import microbench
+                mb = microbench.run(local, reps=128)
+                out["atomic_peaks_ops_per_s"] = mb
+                red_peak = mb["red32_spread_4Mcells"]
+                out["roofline_k3"] = {
+                    "bound": "l2-atomic", "kernel": "gv::k_sweep_walk (one RED.32 per distinct cell per step)",
+                    "achieved": phys / (ms_final * 1e-3), "peak": red_peak, "unit": "RED/s",
+                    "frac": phys / (ms_final * 1e-3) / red_peak,
+                    "peak_source": "gv_microbench_atomics: RED.32, 32 independent L2-resident cells per warp; "
+                                   "the denominator time is the whole raycast+finalise phase"}
+            except Exception as e:  # measurement aid only
+                out["roofline_k3"] = {"error": str(e)}
+            out["parity_sample"] = parity_sample(torch, gv, synth, ctx, dev, wl)
         if world == 1 and not args.no_extra:
             out["other_configs"] = other_configs(torch, gv, synth, ctx, dev)
         if not args.no_cpu and world == 1:
             cores = os.cpu_count() or 1
-            frames = max(2, min(2 * cores, 64))
+            frames = cpu_sample_frames(cores)
             cx, cb = cpu_sample(wl, frames)
             cpu = CpuOracle(wl, cores)
             cpu.run(cx, cb)  # warm-up (page-faults the private grids)
             t = cpu.run(cx, cb)
             out["cpu_baseline"] = {"value": cx.shape[1] / t, "unit": UNIT, "cores": cores, "kind": "port",
                                    "sample": f"{frames} frames ({cx.shape[1]} points), frame-parallel oracle port, "
-                                             f"{t:.2f} s"}
+                                             f"{t:.2f} s, merge+finalise tail {100 * cpu.last_fixed / t:.1f} %",
+                                   "variants": cpu_variants_single_thread(wl, cx, cb),
+                                   "c1_reference_vs_shim": c1_reference_vs_shim()}
         else:
             out["cpu_baseline"] = None
         print(json.dumps(out))

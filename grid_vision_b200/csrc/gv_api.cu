@@ -70,8 +70,10 @@ struct gv_ctx {
   bool multi_checked = false;  // ranks verified to share geometry + pose (gv_grid_finalize_multi)
   bool use_fast = true;  // $GV_NO_FAST=1 forces the generic k_points (A/B measurements)
   int fast_unroll = 2;   // $GV_FAST_U: points per thread per iteration of k_points_fast
+  bool tma_hoist = true; // $GV_TMA_HOIST=0: k_points_tma reads FastHot from the constant bank, 4 CTAs/SM, 2048-point tiles
   bool use_tma = true;   // $GV_NO_TMA=1: k_points_fast (per-tile CTAs, LDG) instead of k_points_tma
-  int fast_agg = 1;      // $GV_FAST_AGG: 0 one RED per beam, 1 match-any groups, 2 adjacent runs
+  int fast_agg = -1;     // $GV_FAST_AGG: 0 one RED per beam, 1 match-any groups, 2 adjacent runs;
+                         // -1: by plane size (L2-resident plane: 0, larger: 2)
   bool l2_persist = true;  // $GV_L2_PERSIST=0: no persisting-L2 window on the end-cell plane
 
   bool has_base = false;
@@ -271,11 +273,12 @@ void mask_geometry(int W, int H, int *shift, int *tx, int *ty)
   *ty = (H + (1 << sh) - 1) >> sh;
 }
 
-int tile_points_for(unsigned long long n, int num_sms)
+int tile_points_for(unsigned long long n, int num_sms, bool big = false, int cap = 4 * kTilePts)
 {
   // bigger CTA tiles amortise the box/mask staging; small clouds keep every SM busy
   const unsigned long long per = n / ((unsigned long long)num_sms * 8ull);
-  if (per >= 4ull * kTilePts) return 4 * kTilePts;
+  if (big && per >= 64ull * kTilePts) return 16 * kTilePts;  // k_points_fast on large batches
+  if (per >= 4ull * kTilePts && cap >= 4 * kTilePts) return 4 * kTilePts;
   if (per >= 2ull * kTilePts) return 2 * kTilePts;
   return kTilePts;
 }
@@ -784,6 +787,7 @@ int gv_create(gv_ctx **out, int device)
   if (const char *u = std::getenv("GV_FAST_U")) ctx->fast_unroll = std::atoi(u);
   if (const char *u = std::getenv("GV_FAST_AGG")) ctx->fast_agg = std::atoi(u);
   ctx->use_tma = std::getenv("GV_NO_TMA") == nullptr;
+  if (const char *u = std::getenv("GV_TMA_HOIST")) ctx->tma_hoist = std::atoi(u) != 0;
   if (const char *u = std::getenv("GV_L2_PERSIST")) ctx->l2_persist = std::atoi(u) != 0;
   if (ctx->l2_persist && prop.persistingL2CacheMaxSize > 0) {
     // room for the end-cell plane of a 2048 x 2048 map (32 MiB) plus slack; larger planes get a
@@ -1554,7 +1558,7 @@ static void fill_fast_args(const PointArgs &a, unsigned *d_defer, FastArgs &f, b
   h.nires = -1.0 / g.res;
   h.Cx = b.c0xd / g.res + (double)bias_cells + magic;
   h.Cy = b.c0yd / g.res + (double)bias_cells + magic;
-  h.kbias = (unsigned)bias_cells << 16;
+  h.kb8 = ((unsigned)bias_cells << 16) + 8u;
   f.hi0 = 0x42380000u;
   f.klim_x = (unsigned)g.nx << 16;
   f.klim_y = (unsigned)g.ny << 16;
@@ -1566,6 +1570,7 @@ static void fill_fast_args(const PointArgs &a, unsigned *d_defer, FastArgs &f, b
   f.c0xf = b.c0xf; f.c0yf = b.c0yf; f.inv_resf = b.inv_resf;
   f.oaxf = b.oaxf; f.oayf = b.oayf;
   f.nxf = (float)g.nx; f.nyf = (float)g.ny;
+  f.nxm1f = (float)(g.nx - 1); f.nym1f = (float)(g.ny - 1);
   f.noaxf = 0.0f - b.oaxf; f.noayf = 0.0f - b.oayf;
   f.paxf = f.nxf - b.oaxf; f.payf = f.nyf - b.oayf;
   f.cam = c;
@@ -1579,17 +1584,26 @@ static int launch_points_fast(gv_ctx *ctx, FastArgs &f, bool bounded, bool tma, 
   f.tile0 = tile0;
   f.ntiles = ntiles;
   const bool lab = f.labels != nullptr, zg = f.bin.use_z_gate != 0;
-  const int U = ctx->fast_unroll, G = ctx->fast_agg;
+  // an end-cell plane that fits L2 absorbs one RED per beam; a larger one pays a DRAM
+  // read-modify-write per RED, so merging the repeats of a warp-row first is worth its instructions
+  const int U = ctx->fast_unroll;
+  const int G = ctx->fast_agg >= 0 ? ctx->fast_agg : (ctx->ncells * sizeof(unsigned long long) > ((size_t)64 << 20) ? 2 : 0);
   if (tma) {
     const size_t stage = 3 * (size_t)f.tile_pts * 4 + kFastBoxes * 16 + (size_t)f.mask_stride * 8;
     const size_t smem = 2 * stage;
-    unsigned grid = 2u * (unsigned)ctx->num_sms;
+    const bool hoist = ctx->tma_hoist;
+    unsigned grid = (hoist ? 2u : 4u) * (unsigned)ctx->num_sms;
     if (grid > ntiles) grid = ntiles;
-#define GV_TMA_LAUNCH(UU, BB, LL, ZZ, GG)                                                            \
+#define GV_TMA_LAUNCH1(UU, BB, LL, ZZ, GG, HH)                                                       \
   do {                                                                                               \
-    GV_CUDA(cudaFuncSetAttribute(k_points_tma<UU, BB, LL, ZZ, GG>,                                    \
+    GV_CUDA(cudaFuncSetAttribute(k_points_tma<UU, BB, LL, ZZ, GG, HH>,                                \
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
-    k_points_tma<UU, BB, LL, ZZ, GG><<<grid, kThreads, smem, ctx->stream>>>(f);                       \
+    k_points_tma<UU, BB, LL, ZZ, GG, HH><<<grid, kThreads, smem, ctx->stream>>>(f);                   \
+  } while (0)
+#define GV_TMA_LAUNCH(UU, BB, LL, ZZ, GG)                \
+  do {                                                   \
+    if (hoist) GV_TMA_LAUNCH1(UU, BB, LL, ZZ, GG, true); \
+    else GV_TMA_LAUNCH1(UU, BB, LL, ZZ, GG, false);      \
   } while (0)
 #define GV_TMA_BL(UU, ZZ, GG)                                  \
   do {                                                         \
@@ -1607,6 +1621,7 @@ static int launch_points_fast(gv_ctx *ctx, FastArgs &f, bool bounded, bool tma, 
     else GV_TMA_BL(2, false, 1);
 #undef GV_TMA_BL
 #undef GV_TMA_LAUNCH
+#undef GV_TMA_LAUNCH1
   } else {
     const size_t smem = (size_t)f.mask_stride * sizeof(unsigned long long);
 #define GV_FAST_LAUNCH(UU, BB, LL, ZZ, GG) k_points_fast<UU, BB, LL, ZZ, GG><<<ntiles, kThreads, smem, ctx->stream>>>(f)
@@ -1667,7 +1682,8 @@ static int process_batch_impl(gv_ctx *ctx, const float *px, const float *py, con
   // points: device-resident, or staged per chunk from host memory
   const uint64_t base = points_on_device ? 0 : p0;  // host path rebases the staged copy to 0
   // tile table: one entry per CTA tile, tiles never straddle frames
-  const int tile_pts = tile_points_for(n, ctx->num_sms);
+  const int tile_pts = tile_points_for(n, ctx->num_sms, ctx->use_fast && !ctx->use_tma,
+                                       ctx->use_fast && ctx->use_tma && !ctx->tma_hoist ? 2 * kTilePts : 4 * kTilePts);
   bool same = ctx->c_valid && ctx->c_tile_pts == tile_pts && (int)ctx->c_boff.size() == nframes + 1 &&
               (int)ctx->c_foff.size() == nframes + 1 &&
               memcmp(ctx->c_boff.data(), box_frame_offsets, ((size_t)nframes + 1) * sizeof(int)) == 0;
@@ -1794,7 +1810,7 @@ static int process_batch_impl(gv_ctx *ctx, const float *px, const float *py, con
     fill_fast_args(a, d_defer, fa, &bounded);
     // bulk copies need 16-byte aligned sources and sizes: plane pointers aligned, every frame
     // boundary (hence every tile start and size) a multiple of 4 points
-    tma = ctx->use_tma && a.vec_ok;
+    tma = ctx->use_tma && a.vec_ok && tile_pts <= 4 * kTilePts;
     for (int f = 0; f <= nframes && tma; ++f) tma = (foff[f] & 3ull) == 0;
   }
   if (points_on_device) {
