@@ -70,7 +70,7 @@ struct gv_ctx {
   bool multi_checked = false;  // ranks verified to share geometry + pose (gv_grid_finalize_multi)
   bool use_fast = true;  // $GV_NO_FAST=1 forces the generic k_points (A/B measurements)
   int fast_unroll = 2;   // $GV_FAST_U: points per thread per iteration of k_points_fast
-  bool tma_hoist = true; // $GV_TMA_HOIST=0: k_points_tma reads FastHot from the constant bank, 4 CTAs/SM, 2048-point tiles
+  bool tma_hoist = false; // $GV_TMA_HOIST=1: k_points_tma keeps FastHot in registers instead of the constant bank
   bool use_tma = true;   // $GV_NO_TMA=1: k_points_fast (per-tile CTAs, LDG) instead of k_points_tma
   int fast_agg = -1;     // $GV_FAST_AGG: 0 one RED per beam, 1 match-any groups, 2 adjacent runs;
                          // -1: by plane size (L2-resident plane: 0, larger: 2)
@@ -89,9 +89,12 @@ struct gv_ctx {
   // calls of a replay: identical offsets skip the upload, the tile-table kernel and any sync)
   std::vector<unsigned long long> c_foff;
   std::vector<int> c_boff;
-  std::vector<unsigned> c_tile_prefix;
+  struct Chunk { int f0, f1; unsigned tile0, ntiles; };
+  std::vector<Chunk> c_chunks;  // frame groups launched together (one for device-resident points)
+  std::vector<unsigned long long> c_tstart, c_tend;  // host images of the tile table (upload source)
+  std::vector<int4> c_tbox;
   int c_tile_pts = 0, c_max_boxes = 0;
-  bool c_valid = false;
+  bool c_on_device = false, c_valid = false;
 
 #ifdef GV_WITH_NCCL
   ncclComm_t comm = nullptr;
@@ -1590,35 +1593,37 @@ static int launch_points_fast(gv_ctx *ctx, FastArgs &f, bool bounded, bool tma, 
   const int G = ctx->fast_agg >= 0 ? ctx->fast_agg : (ctx->ncells * sizeof(unsigned long long) > ((size_t)64 << 20) ? 2 : 0);
   if (tma) {
     const size_t stage = 3 * (size_t)f.tile_pts * 4 + kFastBoxes * 16 + (size_t)f.mask_stride * 8;
-    const size_t smem = 2 * stage;
-    const bool hoist = ctx->tma_hoist;
-    unsigned grid = (hoist ? 2u : 4u) * (unsigned)ctx->num_sms;
+    const size_t smem = 2 * stage + (size_t)f.tile_pts * 8;  // two stages + the run slots
+    // CTA b walks the contiguous table entries [b*K, (b+1)*K): 3 CTAs per SM, and K <= 32768 so
+    // that the 16-bit run counters cannot overflow
+    unsigned grid = 3u * (unsigned)ctx->num_sms;
     if (grid > ntiles) grid = ntiles;
-#define GV_TMA_LAUNCH1(UU, BB, LL, ZZ, GG, HH)                                                       \
+    unsigned K = (ntiles + grid - 1) / grid;
+    if (K > 32768u) K = 32768u;
+    grid = (ntiles + K - 1) / K;
+    f.tiles_per_cta = K;
+    const bool hoist = ctx->tma_hoist;
+#define GV_TMA_LAUNCH1(UU, BB, LL, ZZ, HH)                                                           \
   do {                                                                                               \
-    GV_CUDA(cudaFuncSetAttribute(k_points_tma<UU, BB, LL, ZZ, GG, HH>,                                \
+    GV_CUDA(cudaFuncSetAttribute(k_points_tma<UU, BB, LL, ZZ, HH>,                                    \
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
-    k_points_tma<UU, BB, LL, ZZ, GG, HH><<<grid, kThreads, smem, ctx->stream>>>(f);                   \
+    k_points_tma<UU, BB, LL, ZZ, HH><<<grid, kThreads, smem, ctx->stream>>>(f);                       \
   } while (0)
-#define GV_TMA_LAUNCH(UU, BB, LL, ZZ, GG)                \
-  do {                                                   \
-    if (hoist) GV_TMA_LAUNCH1(UU, BB, LL, ZZ, GG, true); \
-    else GV_TMA_LAUNCH1(UU, BB, LL, ZZ, GG, false);      \
+#define GV_TMA_LAUNCH(UU, BB, LL, ZZ)                \
+  do {                                               \
+    if (hoist) GV_TMA_LAUNCH1(UU, BB, LL, ZZ, true); \
+    else GV_TMA_LAUNCH1(UU, BB, LL, ZZ, false);      \
   } while (0)
-#define GV_TMA_BL(UU, ZZ, GG)                                  \
-  do {                                                         \
-    if (bounded && lab) GV_TMA_LAUNCH(UU, true, true, ZZ, GG); \
-    else if (bounded) GV_TMA_LAUNCH(UU, true, false, ZZ, GG);  \
-    else if (lab) GV_TMA_LAUNCH(UU, false, true, ZZ, GG);      \
-    else GV_TMA_LAUNCH(UU, false, false, ZZ, GG);              \
+#define GV_TMA_BL(UU, ZZ)                                  \
+  do {                                                     \
+    if (bounded && lab) GV_TMA_LAUNCH(UU, true, true, ZZ); \
+    else if (bounded) GV_TMA_LAUNCH(UU, true, false, ZZ);  \
+    else if (lab) GV_TMA_LAUNCH(UU, false, true, ZZ);      \
+    else GV_TMA_LAUNCH(UU, false, false, ZZ);              \
   } while (0)
-    if (zg) GV_TMA_BL(2, true, 1);
-    else if (G == 0 && U == 1) GV_TMA_BL(1, false, 0);
-    else if (G == 0) GV_TMA_BL(2, false, 0);
-    else if (G == 2 && U == 1) GV_TMA_BL(1, false, 2);
-    else if (G == 2) GV_TMA_BL(2, false, 2);
-    else if (U == 1) GV_TMA_BL(1, false, 1);
-    else GV_TMA_BL(2, false, 1);
+    if (zg) GV_TMA_BL(2, true);
+    else if (U == 1) GV_TMA_BL(1, false);
+    else GV_TMA_BL(2, false);
 #undef GV_TMA_BL
 #undef GV_TMA_LAUNCH
 #undef GV_TMA_LAUNCH1
@@ -1681,20 +1686,26 @@ static int process_batch_impl(gv_ctx *ctx, const float *px, const float *py, con
 
   // points: device-resident, or staged per chunk from host memory
   const uint64_t base = points_on_device ? 0 : p0;  // host path rebases the staged copy to 0
-  // tile table: one entry per CTA tile, tiles never straddle frames
+  // Tile table: one entry per tile of tile_pts point indices of one frame (tiles never straddle
+  // frames).  Frames are launched in groups (host path: ~4M-point chunks that pipeline with the
+  // PCIe copies; device path: one group) and within a group the table is COLUMN-MAJOR: the same
+  // block of point indices of consecutive frames sits in consecutive entries, which is what
+  // lets k_points_tma merge a beam with the same beam of the next frame (see gv_points_fast.cuh).
   const int tile_pts = tile_points_for(n, ctx->num_sms, ctx->use_fast && !ctx->use_tma,
-                                       ctx->use_fast && ctx->use_tma && !ctx->tma_hoist ? 2 * kTilePts : 4 * kTilePts);
-  bool same = ctx->c_valid && ctx->c_tile_pts == tile_pts && (int)ctx->c_boff.size() == nframes + 1 &&
-              (int)ctx->c_foff.size() == nframes + 1 &&
+                                       ctx->use_fast && ctx->use_tma ? 2 * kTilePts : 4 * kTilePts);
+  bool same = ctx->c_valid && ctx->c_tile_pts == tile_pts && ctx->c_on_device == points_on_device &&
+              (int)ctx->c_boff.size() == nframes + 1 && (int)ctx->c_foff.size() == nframes + 1 &&
               memcmp(ctx->c_boff.data(), box_frame_offsets, ((size_t)nframes + 1) * sizeof(int)) == 0;
   if (same)
     for (int f = 0; f <= nframes && same; ++f) same = ctx->c_foff[f] == frame_offsets[f] - base;
   if (!same) {
+    // a previous call's asynchronous table upload may still be reading the host images
+    GV_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->c_valid = false;
     ctx->c_foff.resize((size_t)nframes + 1);
     ctx->c_boff.assign(box_frame_offsets, box_frame_offsets + nframes + 1);
-    ctx->c_tile_prefix.resize((size_t)nframes + 1);
     ctx->c_tile_pts = tile_pts;
+    ctx->c_on_device = points_on_device;
     ctx->c_max_boxes = 1;
     unsigned long long ntiles64 = 0;
     for (int f = 0; f < nframes; ++f) {
@@ -1703,28 +1714,53 @@ static int process_batch_impl(gv_ctx *ctx, const float *px, const float *py, con
       const int nb = box_frame_offsets[f + 1] - box_frame_offsets[f];
       GV_REQUIRE(nb >= 0 && nb <= 32767, GV_ERR_INVALID, "frame %d has %d boxes", f, nb);
       if (nb > ctx->c_max_boxes) ctx->c_max_boxes = nb;
-      ctx->c_tile_prefix[f] = (unsigned)ntiles64;
       ntiles64 += (frame_offsets[f + 1] - frame_offsets[f] + tile_pts - 1) / tile_pts;
       GV_REQUIRE(ntiles64 < 2147483647ull, GV_ERR_INVALID, "batch too large");
     }
-    ctx->c_tile_prefix[nframes] = (unsigned)ntiles64;
     for (int f = 0; f <= nframes; ++f) ctx->c_foff[f] = frame_offsets[f] - base;
+    const std::vector<unsigned long long> &fo = ctx->c_foff;
+    ctx->c_chunks.clear();
+    ctx->c_tstart.clear();
+    ctx->c_tend.clear();
+    ctx->c_tbox.clear();
+    ctx->c_tstart.reserve((size_t)ntiles64);
+    ctx->c_tend.reserve((size_t)ntiles64);
+    ctx->c_tbox.reserve((size_t)ntiles64);
+    const uint64_t chunk_pts = 4ull << 20;
+    for (int f0 = 0; f0 < nframes;) {
+      int f1 = f0 + 1;
+      if (points_on_device) f1 = nframes;
+      else while (f1 < nframes && fo[f1 + 1] - fo[f0] <= chunk_pts) ++f1;
+      gv_ctx::Chunk ck{f0, f1, (unsigned)ctx->c_tstart.size(), 0u};
+      unsigned long long maxcols = 0;
+      for (int f = f0; f < f1; ++f) {
+        const unsigned long long cols = (fo[f + 1] - fo[f] + tile_pts - 1) / tile_pts;
+        if (cols > maxcols) maxcols = cols;
+      }
+      for (unsigned long long c = 0; c < maxcols; ++c)
+        for (int f = f0; f < f1; ++f) {
+          const unsigned long long s0 = fo[f] + c * (unsigned long long)tile_pts;
+          if (s0 >= fo[f + 1]) continue;
+          ctx->c_tstart.push_back(s0);
+          ctx->c_tend.push_back(fo[f + 1]);
+          ctx->c_tbox.push_back(make_int4(box_frame_offsets[f], box_frame_offsets[f + 1], f, 0));
+        }
+      ck.ntiles = (unsigned)ctx->c_tstart.size() - ck.tile0;
+      ctx->c_chunks.push_back(ck);
+      f0 = f1;
+    }
   }
   const std::vector<unsigned long long> &foff = ctx->c_foff;
-  const std::vector<unsigned> &tile_prefix = ctx->c_tile_prefix;
   const int max_boxes = ctx->c_max_boxes;
-  const unsigned ntiles = tile_prefix[nframes];
+  const unsigned ntiles = (unsigned)ctx->c_tstart.size();
 
-  unsigned long long *d_foff, *d_tstart, *d_tend;
+  unsigned long long *d_tstart, *d_tend;
   int *d_boff;
-  unsigned *d_tprefix;
   int4 *d_tbox;
-  GV_TRY(reserve_t(ctx, S_FRAME_OFF, (size_t)nframes + 1, &d_foff));
   GV_TRY(reserve_t(ctx, S_BOX_OFF, (size_t)nframes + 1, &d_boff));
-  GV_TRY(reserve_t(ctx, S_TILE_PREFIX, (size_t)nframes + 1, &d_tprefix));
-  GV_TRY(reserve_t(ctx, S_TILE_START, (size_t)ntiles, &d_tstart));
-  GV_TRY(reserve_t(ctx, S_TILE_END, (size_t)ntiles, &d_tend));
-  GV_TRY(reserve_t(ctx, S_TILE_BOX, (size_t)ntiles, &d_tbox));
+  GV_TRY(reserve_t(ctx, S_TILE_START, (size_t)ntiles + 1, &d_tstart));
+  GV_TRY(reserve_t(ctx, S_TILE_END, (size_t)ntiles + 1, &d_tend));
+  GV_TRY(reserve_t(ctx, S_TILE_BOX, (size_t)ntiles + 1, &d_tbox));
 
   const float *d_x = px, *d_y = py, *d_z = pz;
   int16_t *d_lab = labels_out;
@@ -1740,16 +1776,18 @@ static int process_batch_impl(gv_ctx *ctx, const float *px, const float *py, con
   }
 
   if (!same) {
-    // the source vectors are context-owned, so no stream synchronisation is needed here
-    GV_CUDA(cudaMemcpyAsync(d_foff, foff.data(), foff.size() * sizeof(unsigned long long),
-                            cudaMemcpyHostToDevice, ctx->stream));
+    // the source vectors are context-owned and stay untouched until the next layout change
+    // (which synchronises first), so no stream synchronisation is needed here
     GV_CUDA(cudaMemcpyAsync(d_boff, ctx->c_boff.data(), ((size_t)nframes + 1) * sizeof(int),
                             cudaMemcpyHostToDevice, ctx->stream));
-    GV_CUDA(cudaMemcpyAsync(d_tprefix, tile_prefix.data(), tile_prefix.size() * sizeof(unsigned),
-                            cudaMemcpyHostToDevice, ctx->stream));
-    k_build_tiles<<<nframes, 128, 0, ctx->stream>>>(d_foff, d_boff, d_tprefix, nframes, tile_pts,
-                                                   d_tstart, d_tend, d_tbox);
-    GV_LAUNCH_CHECK();
+    if (ntiles) {
+      GV_CUDA(cudaMemcpyAsync(d_tstart, ctx->c_tstart.data(), (size_t)ntiles * sizeof(unsigned long long),
+                              cudaMemcpyHostToDevice, ctx->stream));
+      GV_CUDA(cudaMemcpyAsync(d_tend, ctx->c_tend.data(), (size_t)ntiles * sizeof(unsigned long long),
+                              cudaMemcpyHostToDevice, ctx->stream));
+      GV_CUDA(cudaMemcpyAsync(d_tbox, ctx->c_tbox.data(), (size_t)ntiles * sizeof(int4),
+                              cudaMemcpyHostToDevice, ctx->stream));
+    }
     ctx->c_valid = true;
   }
   float4 *d_f4 = nullptr;
@@ -1810,7 +1848,7 @@ static int process_batch_impl(gv_ctx *ctx, const float *px, const float *py, con
     fill_fast_args(a, d_defer, fa, &bounded);
     // bulk copies need 16-byte aligned sources and sizes: plane pointers aligned, every frame
     // boundary (hence every tile start and size) a multiple of 4 points
-    tma = ctx->use_tma && a.vec_ok && tile_pts <= 4 * kTilePts;
+    tma = ctx->use_tma && a.vec_ok && tile_pts <= 2 * kTilePts;
     for (int f = 0; f <= nframes && tma; ++f) tma = (foff[f] & 3ull) == 0;
   }
   if (points_on_device) {
@@ -1827,13 +1865,9 @@ static int process_batch_impl(gv_ctx *ctx, const float *px, const float *py, con
 
   // host path: pipeline H2D copies, the fused kernel and the label D2H over three streams,
   // a few frames per chunk (~4M points), so PCIe runs in both directions under the compute
-  const uint64_t chunk_pts = 4ull << 20;
   size_t ev = 0;
-  int f0 = 0;
-  while (f0 < nframes) {
-    int f1 = f0 + 1;
-    while (f1 < nframes && foff[f1 + 1] - foff[f0] <= chunk_pts) ++f1;
-    const uint64_t c0 = foff[f0], c1 = foff[f1];
+  for (const gv_ctx::Chunk &ck : ctx->c_chunks) {
+    const uint64_t c0 = foff[ck.f0], c1 = foff[ck.f1];
     const size_t bytes = (size_t)(c1 - c0) * sizeof(float);
     cudaEvent_t e_h2d = get_event(ctx, ev++), e_k = get_event(ctx, ev++);
     GV_REQUIRE(e_h2d && e_k, GV_ERR_CUDA, "cudaEventCreate failed");
@@ -1847,11 +1881,11 @@ static int process_batch_impl(gv_ctx *ctx, const float *px, const float *py, con
     }
     GV_CUDA(cudaEventRecord(e_h2d, ctx->h2d_stream));
     GV_CUDA(cudaStreamWaitEvent(ctx->stream, e_h2d, 0));
-    a.tile0 = tile_prefix[f0];
+    a.tile0 = ck.tile0;
     if (fast) {
-      GV_TRY(launch_points_fast(ctx, fa, bounded, tma, a.tile0, tile_prefix[f1] - tile_prefix[f0]));
+      GV_TRY(launch_points_fast(ctx, fa, bounded, tma, ck.tile0, ck.ntiles));
     } else {
-      GV_TRY(launch_points(ctx, true, true, a, tile_prefix[f1] - tile_prefix[f0], smem));
+      GV_TRY(launch_points(ctx, true, true, a, ck.ntiles, smem));
     }
     if (labels_out && c1 > c0) {
       GV_CUDA(cudaEventRecord(e_k, ctx->stream));
@@ -1859,7 +1893,6 @@ static int process_batch_impl(gv_ctx *ctx, const float *px, const float *py, con
       GV_CUDA(cudaMemcpyAsync(labels_out + p0 + c0, d_lab + c0, (size_t)(c1 - c0) * sizeof(int16_t),
                               cudaMemcpyDeviceToHost, ctx->d2h_stream));
     }
-    f0 = f1;
   }
   if (fast) set_ends_window(ctx, false);
   GV_CUDA(cudaStreamSynchronize(ctx->d2h_stream));

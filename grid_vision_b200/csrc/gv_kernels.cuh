@@ -602,24 +602,6 @@ __global__ void __launch_bounds__(kThreads) k_box_masks(const float4 *__restrict
   }
 }
 
-// per-frame tile table for batch mode: one CTA per frame
-__global__ void k_build_tiles(const unsigned long long *frame_offsets, const int *box_frame_offsets,
-                              const unsigned *tile_prefix, int nframes,
-                              int tile_pts, unsigned long long *tile_start,
-                              unsigned long long *tile_end, int4 *tile_boxes)
-{
-  const int f = blockIdx.x;
-  if (f >= nframes) return;
-  const unsigned long long s = frame_offsets[f], e = frame_offsets[f + 1];
-  const unsigned t0 = tile_prefix[f], t1 = tile_prefix[f + 1];
-  const int4 br = make_int4(box_frame_offsets[f], box_frame_offsets[f + 1], f, 0);
-  for (unsigned t = t0 + threadIdx.x; t < t1; t += blockDim.x) {
-    tile_start[t] = s + (unsigned long long)(t - t0) * (unsigned)tile_pts;
-    tile_end[t] = e;
-    tile_boxes[t] = br;
-  }
-}
-
 // N4: pcl::PointXYZI 32-byte AoS -> SoA planes (ref: pcl::fromROSMsg output consumed at
 // src/grid_vision_node.cpp:103-106,157)
 __global__ void __launch_bounds__(kThreads) k_aos32_to_soa(const float4 *__restrict__ pts,

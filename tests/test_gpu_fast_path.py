@@ -172,9 +172,10 @@ def test_fast_path_index_adversarial(ctx, geom):
 
 
 # ----------------------------------------------------------------- template variants
-VARIANTS = [{"GV_FAST_U": "1"}, {"GV_FAST_U": "4"}, {"GV_FAST_AGG": "0"}, {"GV_FAST_AGG": "2"},
-            {"GV_FAST_AGG": "2", "GV_FAST_U": "1"}, {"GV_NO_TMA": "1"}, {"GV_NO_TMA": "1", "GV_FAST_AGG": "0"},
-            {"GV_NO_TMA": "1", "GV_FAST_AGG": "2", "GV_FAST_U": "4"}, {"GV_L2_PERSIST": "0"}]
+VARIANTS = [{"GV_FAST_U": "1"}, {"GV_TMA_HOIST": "1"}, {"GV_TMA_HOIST": "1", "GV_FAST_U": "1"},
+            {"GV_NO_TMA": "1"}, {"GV_NO_TMA": "1", "GV_FAST_AGG": "0", "GV_FAST_U": "1"},
+            {"GV_NO_TMA": "1", "GV_FAST_AGG": "1"}, {"GV_NO_TMA": "1", "GV_FAST_AGG": "2", "GV_FAST_U": "4"},
+            {"GV_L2_PERSIST": "0"}]
 
 
 @pytest.mark.parametrize("env", VARIANTS, ids=lambda e: ",".join(f"{k[3:]}={v}" for k, v in e.items()))
