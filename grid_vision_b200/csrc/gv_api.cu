@@ -33,7 +33,7 @@ enum {
   S_X, S_Y, S_Z, S_AOS, S_LAB, S_PIX, S_UV, S_BOX_RAW, S_BOX_F4, S_FRAME_OFF, S_BOX_OFF,
   S_TILE_PREFIX, S_TILE_START, S_TILE_END, S_TILE_BOX, S_CELL, S_FLAGS, S_FOOT_IN, S_FOOT_LAB,
   S_RECT, S_SMALL, S_OX, S_OY, S_OZ, S_SCAN0, S_SCAN1, S_SCAN2, S_SCAN3, S_UVZ, S_INDICES,
-  S_LABELS_IN, S_MASKS, S_SET_OFF, S_SWEEP, S_SWEEP_PREFIX, S_BATCH_ENTRY, S_BATCH_MI, S_BATCH_W, S_N2_TAB, S_N2_KEEP, S_N2_OUT, S_N2_OFF, S_N1_PLANES, S_N1_VALID, S_N1_SCORES, S_N1_STATE, S_DEFER, S_COUNT
+  S_LABELS_IN, S_MASKS, S_SET_OFF, S_SWEEP, S_SWEEP_PREFIX, S_BATCH_ENTRY, S_BATCH_MI, S_BATCH_W, S_N2_TAB, S_N2_KEEP, S_N2_OUT, S_N2_OFF, S_N1_PLANES, S_N1_VALID, S_N1_SCORES, S_N1_STATE, S_DEFER, S_FRAMES, S_COUNT
 };
 
 constexpr size_t kPlanePad = 4096;  // slack cells so multi-GPU slabs can be equal-sized
@@ -70,6 +70,7 @@ struct gv_ctx {
   bool multi_checked = false;  // ranks verified to share geometry + pose (gv_grid_finalize_multi)
   bool use_fast = true;  // $GV_NO_FAST=1 forces the generic k_points (A/B measurements)
   int fast_unroll = 2;   // $GV_FAST_U: points per thread per iteration of k_points_fast
+  int fast_kind = 0;     // $GV_FAST_KIND: 0 k_points_col (default), 1 k_points_tma, 2 k_points_fast
   bool tma_hoist = false; // $GV_TMA_HOIST=1: k_points_tma keeps FastHot in registers instead of the constant bank
   bool use_tma = true;   // $GV_NO_TMA=1: k_points_fast (per-tile CTAs, LDG) instead of k_points_tma
   int fast_agg = -1;     // $GV_FAST_AGG: 0 one RED per beam, 1 match-any groups, 2 adjacent runs;
@@ -93,6 +94,8 @@ struct gv_ctx {
   std::vector<Chunk> c_chunks;  // frame groups launched together (one for device-resident points)
   std::vector<unsigned long long> c_tstart, c_tend;  // host images of the tile table (upload source)
   std::vector<int4> c_tbox;
+  std::vector<uint4> c_frames;   // per-frame records for k_points_col
+  unsigned c_max_pts = 0;        // largest frame (points)
   int c_tile_pts = 0, c_max_boxes = 0;
   bool c_on_device = false, c_valid = false;
 
@@ -790,6 +793,8 @@ int gv_create(gv_ctx **out, int device)
   if (const char *u = std::getenv("GV_FAST_U")) ctx->fast_unroll = std::atoi(u);
   if (const char *u = std::getenv("GV_FAST_AGG")) ctx->fast_agg = std::atoi(u);
   ctx->use_tma = std::getenv("GV_NO_TMA") == nullptr;
+  if (const char *u = std::getenv("GV_FAST_KIND")) ctx->fast_kind = std::atoi(u);
+  if (ctx->fast_kind != 1) ctx->use_tma = false;
   if (const char *u = std::getenv("GV_TMA_HOIST")) ctx->tma_hoist = std::atoi(u) != 0;
   if (const char *u = std::getenv("GV_L2_PERSIST")) ctx->l2_persist = std::atoi(u) != 0;
   if (ctx->l2_persist && prop.persistingL2CacheMaxSize > 0) {
@@ -1661,6 +1666,46 @@ static int launch_points_fast(gv_ctx *ctx, FastArgs &f, bool bounded, bool tma, 
   return GV_OK;
 }
 
+// k_points_col over frames [frame0, frame0 + nframes): grid = (column blocks, frame groups)
+static int launch_points_col(gv_ctx *ctx, FastArgs &f, bool bounded, int frame0, int nframes, unsigned max_pts)
+{
+  if (nframes <= 0 || max_pts == 0) return GV_OK;
+  f.frame0 = frame0;
+  f.nframes = nframes;
+  const unsigned cols = (max_pts + kThreads - 1) / kThreads;
+  // enough CTAs for ~16 waves of 5 CTAs per SM, as few frame groups as that allows: the longer a
+  // thread stays on its beam index, the more of the beam's repeats it merges before the RED
+  const unsigned want = (unsigned)ctx->num_sms * 5u * 16u;
+  unsigned groups = (want + cols - 1) / cols;
+  if (groups > (unsigned)nframes) groups = (unsigned)nframes;
+  if (groups < 1u) groups = 1u;
+  if (groups > 65535u) groups = 65535u;
+  f.frames_per_cta = (nframes + (int)groups - 1) / (int)groups;
+  groups = (unsigned)((nframes + f.frames_per_cta - 1) / f.frames_per_cta);
+  const dim3 grid(cols, groups);
+  const bool lab = f.labels != nullptr, zg = f.bin.use_z_gate != 0;
+#define GV_COL_LAUNCH(BB, LL, ZZ) k_points_col<BB, LL, ZZ><<<grid, kThreads, 0, ctx->stream>>>(f)
+#define GV_COL_BL(ZZ)                                  \
+  do {                                                 \
+    if (bounded && lab) GV_COL_LAUNCH(true, true, ZZ); \
+    else if (bounded) GV_COL_LAUNCH(true, false, ZZ);  \
+    else if (lab) GV_COL_LAUNCH(false, true, ZZ);      \
+    else GV_COL_LAUNCH(false, false, ZZ);              \
+  } while (0)
+  if (zg) GV_COL_BL(true);
+  else GV_COL_BL(false);
+#undef GV_COL_BL
+#undef GV_COL_LAUNCH
+  GV_LAUNCH_CHECK();
+  const unsigned long long nwords = (unsigned long long)nframes * f.defer_stride;
+  unsigned nb = (unsigned)((nwords + kThreads - 1) / kThreads);
+  const unsigned cap = (unsigned)ctx->num_sms * 16u;
+  if (nb > cap) nb = cap;
+  k_points_deferred<<<nb, kThreads, 0, ctx->stream>>>(f);
+  GV_LAUNCH_CHECK();
+  return GV_OK;
+}
+
 // ---- batch: the whole hot path, one kernel pass over the points ------------------------
 static int process_batch_impl(gv_ctx *ctx, const float *px, const float *py, const float *pz,
                               bool points_on_device, const uint64_t *frame_offsets, int nframes,
@@ -1719,6 +1764,15 @@ static int process_batch_impl(gv_ctx *ctx, const float *px, const float *py, con
     }
     for (int f = 0; f <= nframes; ++f) ctx->c_foff[f] = frame_offsets[f] - base;
     const std::vector<unsigned long long> &fo = ctx->c_foff;
+    ctx->c_frames.resize((size_t)nframes);
+    ctx->c_max_pts = 0;
+    for (int f = 0; f < nframes; ++f) {
+      const unsigned long long np = fo[f + 1] - fo[f];
+      GV_REQUIRE(np < 4294967295ull, GV_ERR_INVALID, "frame %d too large", f);
+      if (np > ctx->c_max_pts) ctx->c_max_pts = (unsigned)np;
+      ctx->c_frames[f] = make_uint4((unsigned)(fo[f] & 0xffffffffull), (unsigned)(fo[f] >> 32), (unsigned)np,
+                                    (unsigned)box_frame_offsets[f]);
+    }
     ctx->c_chunks.clear();
     ctx->c_tstart.clear();
     ctx->c_tend.clear();
@@ -1761,6 +1815,8 @@ static int process_batch_impl(gv_ctx *ctx, const float *px, const float *py, con
   GV_TRY(reserve_t(ctx, S_TILE_START, (size_t)ntiles + 1, &d_tstart));
   GV_TRY(reserve_t(ctx, S_TILE_END, (size_t)ntiles + 1, &d_tend));
   GV_TRY(reserve_t(ctx, S_TILE_BOX, (size_t)ntiles + 1, &d_tbox));
+  uint4 *d_frames;
+  GV_TRY(reserve_t(ctx, S_FRAMES, (size_t)nframes + 1, &d_frames));
 
   const float *d_x = px, *d_y = py, *d_z = pz;
   int16_t *d_lab = labels_out;
@@ -1779,6 +1835,8 @@ static int process_batch_impl(gv_ctx *ctx, const float *px, const float *py, con
     // the source vectors are context-owned and stay untouched until the next layout change
     // (which synchronises first), so no stream synchronisation is needed here
     GV_CUDA(cudaMemcpyAsync(d_boff, ctx->c_boff.data(), ((size_t)nframes + 1) * sizeof(int),
+                            cudaMemcpyHostToDevice, ctx->stream));
+    GV_CUDA(cudaMemcpyAsync(d_frames, ctx->c_frames.data(), (size_t)nframes * sizeof(uint4),
                             cudaMemcpyHostToDevice, ctx->stream));
     if (ntiles) {
       GV_CUDA(cudaMemcpyAsync(d_tstart, ctx->c_tstart.data(), (size_t)ntiles * sizeof(unsigned long long),
@@ -1838,7 +1896,9 @@ static int process_batch_impl(gv_ctx *ctx, const float *px, const float *py, con
   if (fast) {
     // ballot-word bitmap of deferred points: all-zero between launches (k_points_deferred clears
     // what k_points_fast set), so it is zeroed only when the slot is (re)allocated
-    const size_t nwords = (size_t)ntiles * (size_t)(tile_pts >> 5);
+    const bool col = ctx->fast_kind == 0;
+    const unsigned defer_stride = (ctx->c_max_pts + 31u) / 32u;
+    const size_t nwords = col ? (size_t)nframes * defer_stride : (size_t)ntiles * (size_t)(tile_pts >> 5);
     unsigned *d_defer = nullptr;
     const void *before = ctx->s[S_DEFER].p;
     const size_t cap_before = ctx->s[S_DEFER].cap;
@@ -1846,6 +1906,9 @@ static int process_batch_impl(gv_ctx *ctx, const float *px, const float *py, con
     if (ctx->s[S_DEFER].p != before || ctx->s[S_DEFER].cap != cap_before)
       GV_CUDA(cudaMemsetAsync(d_defer, 0, ctx->s[S_DEFER].cap, ctx->stream));
     fill_fast_args(a, d_defer, fa, &bounded);
+    fa.frames = d_frames;
+    fa.defer_stride = defer_stride;
+    fa.col_mode = col ? 1 : 0;
     // bulk copies need 16-byte aligned sources and sizes: plane pointers aligned, every frame
     // boundary (hence every tile start and size) a multiple of 4 points
     tma = ctx->use_tma && a.vec_ok && tile_pts <= 2 * kTilePts;
@@ -1855,7 +1918,8 @@ static int process_batch_impl(gv_ctx *ctx, const float *px, const float *py, con
     a.tile0 = 0;
     if (fast) {
       set_ends_window(ctx, true);
-      const int rc = launch_points_fast(ctx, fa, bounded, tma, 0, ntiles);
+      const int rc = fa.col_mode ? launch_points_col(ctx, fa, bounded, 0, nframes, ctx->c_max_pts)
+                                 : launch_points_fast(ctx, fa, bounded, tma, 0, ntiles);
       set_ends_window(ctx, false);
       return rc;
     }
@@ -1883,7 +1947,8 @@ static int process_batch_impl(gv_ctx *ctx, const float *px, const float *py, con
     GV_CUDA(cudaStreamWaitEvent(ctx->stream, e_h2d, 0));
     a.tile0 = ck.tile0;
     if (fast) {
-      GV_TRY(launch_points_fast(ctx, fa, bounded, tma, ck.tile0, ck.ntiles));
+      if (fa.col_mode) GV_TRY(launch_points_col(ctx, fa, bounded, ck.f0, ck.f1 - ck.f0, ctx->c_max_pts));
+      else GV_TRY(launch_points_fast(ctx, fa, bounded, tma, ck.tile0, ck.ntiles));
     } else {
       GV_TRY(launch_points(ctx, true, true, a, ck.ntiles, smem));
     }

@@ -172,16 +172,18 @@ def test_fast_path_index_adversarial(ctx, geom):
 
 
 # ----------------------------------------------------------------- template variants
-VARIANTS = [{"GV_FAST_U": "1"}, {"GV_TMA_HOIST": "1"}, {"GV_TMA_HOIST": "1", "GV_FAST_U": "1"},
-            {"GV_NO_TMA": "1"}, {"GV_NO_TMA": "1", "GV_FAST_AGG": "0", "GV_FAST_U": "1"},
-            {"GV_NO_TMA": "1", "GV_FAST_AGG": "1"}, {"GV_NO_TMA": "1", "GV_FAST_AGG": "2", "GV_FAST_U": "4"},
-            {"GV_L2_PERSIST": "0"}]
+VARIANTS = [{"GV_FAST_KIND": "0"}, {"GV_FAST_KIND": "1"}, {"GV_FAST_KIND": "1", "GV_FAST_U": "1"},
+            {"GV_FAST_KIND": "1", "GV_TMA_HOIST": "1"}, {"GV_FAST_KIND": "2"},
+            {"GV_FAST_KIND": "2", "GV_FAST_AGG": "0", "GV_FAST_U": "1"}, {"GV_FAST_KIND": "2", "GV_FAST_AGG": "1"},
+            {"GV_FAST_KIND": "2", "GV_FAST_AGG": "2", "GV_FAST_U": "4"}, {"GV_L2_PERSIST": "0"}]
 
 
 @pytest.mark.parametrize("env", VARIANTS, ids=lambda e: ",".join(f"{k[3:]}={v}" for k, v in e.items()))
 def test_fast_path_kernel_variants(env):
-    """Every instantiation family (points per thread, RED aggregation mode, TMA-fed persistent kernel
-    vs per-tile LDG kernel, L2 window) on three frame layouts: arbitrary ragged sizes (LDG kernel:
+    """Every fast kernel (KIND 0 k_points_col: one thread per beam index across frames, run-length
+    binning in registers; 1 k_points_tma: persistent, bulk-copy fed, run slots in shared memory;
+    2 k_points_fast: one CTA per tile, optional warp-level RED merging) and instantiation family
+    on three frame layouts: arbitrary ragged sizes (LDG kernel:
     bulk copies need 4-point alignment), ragged sizes that are multiples of 4 (TMA kernel, partial
     last rows), and one-point / empty frames."""
     os.environ.update(env)
