@@ -70,6 +70,7 @@ struct gv_ctx {
   bool multi_checked = false;  // ranks verified to share geometry + pose (gv_grid_finalize_multi)
   bool use_fast = true;  // $GV_NO_FAST=1 forces the generic k_points (A/B measurements)
   int fast_unroll = 2;   // $GV_FAST_U: points per thread per iteration of k_points_fast
+  bool col_hoist = true; // $GV_COL_HOIST=0: k_points_col reads FastHot from the constant bank
   int fast_kind = 0;     // $GV_FAST_KIND: 0 k_points_col (default), 1 k_points_tma, 2 k_points_fast
   bool tma_hoist = false; // $GV_TMA_HOIST=1: k_points_tma keeps FastHot in registers instead of the constant bank
   bool use_tma = true;   // $GV_NO_TMA=1: k_points_fast (per-tile CTAs, LDG) instead of k_points_tma
@@ -794,6 +795,7 @@ int gv_create(gv_ctx **out, int device)
   if (const char *u = std::getenv("GV_FAST_AGG")) ctx->fast_agg = std::atoi(u);
   ctx->use_tma = std::getenv("GV_NO_TMA") == nullptr;
   if (const char *u = std::getenv("GV_FAST_KIND")) ctx->fast_kind = std::atoi(u);
+  if (const char *u = std::getenv("GV_COL_HOIST")) ctx->col_hoist = std::atoi(u) != 0;
   if (ctx->fast_kind != 1) ctx->use_tma = false;
   if (const char *u = std::getenv("GV_TMA_HOIST")) ctx->tma_hoist = std::atoi(u) != 0;
   if (const char *u = std::getenv("GV_L2_PERSIST")) ctx->l2_persist = std::atoi(u) != 0;
@@ -1535,18 +1537,20 @@ static void fill_fast_args(const PointArgs &a, unsigned *d_defer, FastArgs &f, b
   f.mask_stride = a.mask_stride;
   f.mask_shift = a.mask_shift[0];
   f.mask_tx = a.mask_tx[0];
-  for (int i = 0; i < 12; ++i) h.Tc[i] = c.T[i];
+  FastWarm &w = f.warm;
+  for (int i = 0; i < 8; ++i) w.Tcxy[i] = c.T[i];
+  for (int i = 0; i < 4; ++i) h.Tcz[i] = c.T[8 + i];
   for (int i = 0; i < 8; ++i) h.Tb[i] = b.T[i];
   for (int i = 0; i < 4; ++i) f.Tbz[i] = b.T[8 + i];
-  h.fx = c.fxf; h.fy = c.fyf; h.cx = c.cxf; h.cy = c.cyf;
+  w.fx = c.fxf; w.fy = c.fyf; w.cx = c.cxf; w.cy = c.cyf;
   // E(q) = 2^-22 (6|q| + 1.5|c| + 1), see fast_point
   const float u22 = 2.384185791015625e-07f;
-  h.e6 = 6.0f * u22;
-  h.e0u = u22 * (1.5f * std::fabs(c.cxf) + 1.0f) * 1.0001f;
-  h.e0v = u22 * (1.5f * std::fabs(c.cyf) + 1.0f) * 1.0001f;
-  h.Wf = c.Wf; h.Hf = c.Hf;
+  w.e6 = 6.0f * u22;
+  w.e0u = u22 * (1.5f * std::fabs(c.cxf) + 1.0f) * 1.0001f;
+  w.e0v = u22 * (1.5f * std::fabs(c.cyf) + 1.0f) * 1.0001f;
+  w.Wf = c.Wf; w.Hf = c.Hf;
   h.oxf = b.oxf; h.oyf = b.oyf;
-  h.rmaxf = b.rmaxf;
+  w.rmaxf = b.rmaxf;
   h.rmax2f = b.cap ? b.rmax2f : INFINITY;
   h.lab_min = b.occ_mode == 1 ? 0 : -1;
   f.z_min = b.z_min; f.z_max = b.z_max;
@@ -1681,10 +1685,20 @@ static int launch_points_col(gv_ctx *ctx, FastArgs &f, bool bounded, int frame0,
   if (groups < 1u) groups = 1u;
   if (groups > 65535u) groups = 65535u;
   f.frames_per_cta = (nframes + (int)groups - 1) / (int)groups;
+  // records are staged per CTA (kColFrames) with 32-bit element offsets relative to the group's
+  // first frame: a group may not span 2^32 points
+  if (f.frames_per_cta > kColFrames) f.frames_per_cta = kColFrames;
+  while (f.frames_per_cta > 1 && (unsigned long long)f.frames_per_cta * max_pts >= 4294967295ull) f.frames_per_cta /= 2;
   groups = (unsigned)((nframes + f.frames_per_cta - 1) / f.frames_per_cta);
+  GV_REQUIRE(groups <= 65535u, GV_ERR_INVALID, "too many frames for one launch (%d)", nframes);
   const dim3 grid(cols, groups);
   const bool lab = f.labels != nullptr, zg = f.bin.use_z_gate != 0;
-#define GV_COL_LAUNCH(BB, LL, ZZ) k_points_col<BB, LL, ZZ><<<grid, kThreads, 0, ctx->stream>>>(f)
+  const bool hoist = ctx->col_hoist;
+#define GV_COL_LAUNCH(BB, LL, ZZ)                                                  \
+  do {                                                                             \
+    if (hoist) k_points_col<BB, LL, ZZ, true><<<grid, kThreads, 0, ctx->stream>>>(f); \
+    else k_points_col<BB, LL, ZZ, false><<<grid, kThreads, 0, ctx->stream>>>(f);      \
+  } while (0)
 #define GV_COL_BL(ZZ)                                  \
   do {                                                 \
     if (bounded && lab) GV_COL_LAUNCH(true, true, ZZ); \

@@ -172,7 +172,7 @@ def test_fast_path_index_adversarial(ctx, geom):
 
 
 # ----------------------------------------------------------------- template variants
-VARIANTS = [{"GV_FAST_KIND": "0"}, {"GV_FAST_KIND": "1"}, {"GV_FAST_KIND": "1", "GV_FAST_U": "1"},
+VARIANTS = [{"GV_FAST_KIND": "0"}, {"GV_COL_HOIST": "0"}, {"GV_FAST_KIND": "1"}, {"GV_FAST_KIND": "1", "GV_FAST_U": "1"},
             {"GV_FAST_KIND": "1", "GV_TMA_HOIST": "1"}, {"GV_FAST_KIND": "2"},
             {"GV_FAST_KIND": "2", "GV_FAST_AGG": "0", "GV_FAST_U": "1"}, {"GV_FAST_KIND": "2", "GV_FAST_AGG": "1"},
             {"GV_FAST_KIND": "2", "GV_FAST_AGG": "2", "GV_FAST_U": "4"}, {"GV_L2_PERSIST": "0"}]
