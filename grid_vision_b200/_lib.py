@@ -44,13 +44,13 @@ class LShape(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("beams", C.c_uint64), ("cells_logical", C.c_uint64),
                 ("cells_physical", C.c_uint64), ("distinct_ends", C.c_uint64),
-                ("kernel_launches", C.c_uint64)]
+                ("kernel_launches", C.c_uint64), ("merges", C.c_uint64), ("merge_ms_last", C.c_double)]
 
 
 # every symbol include/gridvision_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "gv_version", "gv_status_string", "gv_create", "gv_destroy", "gv_last_error",
-    "gv_synchronize", "gv_stream", "gv_set_stream", "gv_get_stats",
+    "gv_synchronize", "gv_join", "gv_stream", "gv_set_stream", "gv_get_stats",
     "gv_set_cameras", "gv_fuse", "gv_fuse_aos32", "gv_fuse_dev", "gv_transform_points",
     "gv_project_kdtree", "gv_partition_by_label", "gv_segment_ground", "gv_bbox_pose",
     "gv_grid_init_reference", "gv_grid_init", "gv_grid_get_desc", "gv_grid_reset",

@@ -89,7 +89,11 @@ class Context:
     def stats(self) -> dict:
         st = Stats()
         self._check(self._lib.gv_get_stats(self._h, C.byref(st)), "gv_get_stats")
-        return {k: int(getattr(st, k)) for k, _ in Stats._fields_}
+        return {k: (float(getattr(st, k)) if k == "merge_ms_last" else int(getattr(st, k))) for k, _ in Stats._fields_}
+
+    def join(self):
+        """The context stream waits for the merge (finalize) still running on the internal stream."""
+        self._check(self._lib.gv_join(self._h), "gv_join")
 
     # ------------------------------------------------------------------ fusion
     def set_cameras(self, K, wh, T_cam_lidar=None):
@@ -349,12 +353,12 @@ class Context:
         return buf.raw
 
     def ipc_export(self) -> bytes:
-        buf = C.create_string_buffer(320)
+        buf = C.create_string_buffer(448)
         self._check(self._lib.gv_ipc_export(self._h, buf), "gv_ipc_export")
         return buf.raw
 
     def ipc_import(self, blobs: bytes, world: int, rank: int):
-        assert len(blobs) == 320 * world
+        assert len(blobs) == 448 * world
         self._check(self._lib.gv_ipc_import(self._h, C.c_char_p(blobs), C.c_int(world), C.c_int(rank)),
                     "gv_ipc_import")
 

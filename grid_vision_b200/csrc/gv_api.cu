@@ -60,7 +60,18 @@ struct gv_ctx {
   size_t ncells = 0;
   float *d_lo = nullptr, *d_occ = nullptr;
   int32_t *d_hit = nullptr, *d_miss = nullptr;
+  // Two end-cell planes: beams are binned into d_ends (= d_ends_buf[ends_cur]) on the caller's
+  // stream while the previous batch's plane is merged (raycast + [exchange] + finalise) on
+  // merge_stream.  ev_merge_done[i] / merge_busy[i]: the merge that consumed plane i.
   unsigned long long *d_ends = nullptr;
+  unsigned long long *d_ends_buf[2] = {nullptr, nullptr};
+  int ends_cur = 0;
+  cudaStream_t merge_stream = nullptr;
+  cudaEvent_t ev_bin_done = nullptr, ev_merge_done[2] = {nullptr, nullptr};
+  cudaEvent_t ev_merge_t0 = nullptr, ev_merge_t1 = nullptr;  // timing of the last merge
+  bool merge_busy[2] = {false, false}, merge_timed = false;
+  bool overlap = true;  // $GV_OVERLAP=0: finalize runs on the caller's stream
+  unsigned long long merges = 0;
   unsigned *d_list_count = nullptr;  // work-item counter of the raycast sweep
   SweepEntry *d_sweep = nullptr;     // sweep table for the current start cell
   unsigned *d_sweep_prefix = nullptr;  // [n_sweep+1] first work item of each entry
@@ -70,7 +81,7 @@ struct gv_ctx {
   bool multi_checked = false;  // ranks verified to share geometry + pose (gv_grid_finalize_multi)
   bool use_fast = true;  // $GV_NO_FAST=1 forces the generic k_points (A/B measurements)
   int fast_unroll = 2;   // $GV_FAST_U: points per thread per iteration of k_points_fast
-  bool col_hoist = true; // $GV_COL_HOIST=0: k_points_col reads FastHot from the constant bank
+  bool col_hoist = false; // $GV_COL_HOIST=1: k_points_col keeps FastHot in registers (fewer instructions, 3 CTAs/SM)
   int fast_kind = 0;     // $GV_FAST_KIND: 0 k_points_col (default), 1 k_points_tma, 2 k_points_fast
   bool tma_hoist = false; // $GV_TMA_HOIST=1: k_points_tma keeps FastHot in registers instead of the constant bank
   bool use_tma = true;   // $GV_NO_TMA=1: k_points_fast (per-tile CTAs, LDG) instead of k_points_tma
@@ -106,7 +117,10 @@ struct gv_ctx {
   int rank = 0, world = 1;
   // peer-memory (cudaIpc) views of every rank's planes; [rank] is the local pointer
   bool p2p = false;
-  Peers<unsigned long long> peer_ends{};
+  Peers<unsigned long long> peer_ends{}, peer_ends_buf[2] = {};
+  unsigned *d_flags = nullptr;  // [kMaxPeers] arrival epochs of k_peer_barrier, [kMaxPeers] = timeout flag
+  Peers<unsigned> peer_flags{};
+  unsigned barrier_epoch = 0;
   Peers<int32_t> peer_hit{}, peer_miss{};
   Peers<float> peer_lo{}, peer_occ{};
   int *d_barrier = nullptr;
@@ -182,6 +196,7 @@ int reserve(gv_ctx *ctx, int slot, size_t bytes, void **out)
   if (s.cap < bytes) {
     // growing a scratch slot may free memory a previous async kernel still reads
     GV_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->merge_stream && ctx->merge_stream != ctx->stream) GV_CUDA(cudaStreamSynchronize(ctx->merge_stream));
     if (s.p) GV_CUDA(cudaFree(s.p));
     s.p = nullptr;
     s.cap = 0;
@@ -210,6 +225,78 @@ cudaEvent_t get_event(gv_ctx *ctx, size_t i)
     ctx->events.push_back(e);
   }
   return ctx->events[i];
+}
+
+// The caller's stream waits for every merge still in flight on merge_stream (grid state, count
+// planes and both end-cell planes are then safe to touch from the caller's stream).
+int join_merge(gv_ctx *ctx)
+{
+  for (int i = 0; i < 2; ++i)
+    if (ctx->merge_busy[i]) {
+      GV_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_merge_done[i], 0));
+      ctx->merge_busy[i] = false;
+    }
+  return GV_OK;
+}
+
+// Before binning into the current end-cell plane: its previous merge (two batches ago) is done.
+int bin_begin(gv_ctx *ctx)
+{
+  const int i = ctx->ends_cur;
+  if (ctx->merge_busy[i]) {
+    GV_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_merge_done[i], 0));
+    ctx->merge_busy[i] = false;
+  }
+  return GV_OK;
+}
+
+// k_peer_barrier gave up waiting for a rank (it raises the word after the arrival slots)
+int check_barrier_timeout(gv_ctx *ctx)
+{
+  if (!ctx->p2p) return GV_OK;
+  unsigned flag = 0;
+  GV_CUDA(cudaMemcpy(&flag, ctx->d_flags + kMaxPeers, sizeof(flag), cudaMemcpyDeviceToHost));
+  GV_REQUIRE(flag == 0u, GV_ERR_STATE, "a peer-memory barrier timed out: some rank did not reach gv_grid_finalize_multi");
+  return GV_OK;
+}
+
+// The merge of the batch binned so far runs on merge_stream (ordered after the binning, which is
+// on the caller's stream), so that the caller's next batch can be binned into the other plane
+// meanwhile.  merge_begin redirects the context stream; merge_end restores it and flips planes.
+struct MergeScope {
+  cudaStream_t saved;
+  bool active;
+};
+
+int merge_begin(gv_ctx *ctx, MergeScope *sc)
+{
+  sc->saved = ctx->stream;
+  sc->active = ctx->overlap && ctx->merge_stream != nullptr;
+  if (!sc->active) return join_merge(ctx);
+  GV_CUDA(cudaEventRecord(ctx->ev_bin_done, ctx->stream));
+  GV_CUDA(cudaStreamWaitEvent(ctx->merge_stream, ctx->ev_bin_done, 0));
+  ctx->stream = ctx->merge_stream;
+  GV_CUDA(cudaEventRecord(ctx->ev_merge_t0, ctx->stream));
+  return GV_OK;
+}
+
+int merge_end(gv_ctx *ctx, MergeScope *sc, int rc)
+{
+  if (sc->active) {
+    if (rc == GV_OK) {
+      cudaEventRecord(ctx->ev_merge_t1, ctx->stream);
+      ctx->merge_timed = true;
+    }
+    const int i = ctx->ends_cur;
+    cudaEventRecord(ctx->ev_merge_done[i], ctx->stream);
+    ctx->merge_busy[i] = true;
+    ctx->stream = sc->saved;
+    ctx->ends_cur ^= 1;
+    ctx->d_ends = ctx->d_ends_buf[ctx->ends_cur];
+    ctx->peer_ends = ctx->peer_ends_buf[ctx->ends_cur];
+  }
+  ctx->merges++;
+  return rc;
 }
 
 inline unsigned blocks_for(unsigned long long n, unsigned per_block)
@@ -441,6 +528,7 @@ int accumulate_dev_impl(gv_ctx *ctx, const float *d_x, const float *d_y, const f
   GV_REQUIRE(prm->occ_mode != GV_OCC_LABELLED || d_labels != nullptr, GV_ERR_INVALID,
              "GV_OCC_LABELLED needs labels");
   GV_TRY(note_beams(ctx, n));
+  GV_TRY(bin_begin(ctx));
   a.labels_in = d_labels;
   a.ends = ctx->d_ends;
   a.cell_out = d_cell;
@@ -463,27 +551,26 @@ int raycast_flush_impl(gv_ctx *ctx, unsigned rank, unsigned world, bool p2p_gath
   GV_TRY(reserve_t(ctx, S_BATCH_ENTRY, max_batches, &d_bentry));
   GV_TRY(reserve_t(ctx, S_BATCH_MI, max_batches * 32, &d_bmi));
   GV_TRY(reserve_t(ctx, S_BATCH_W, max_batches * 32, &d_bw));
-  if (p2p_gather) {
-    // fused all-reduce of the ends plane, restricted to the cells whose lines this rank walks
-    k_ends_gather<<<nb, kThreads, 0, ctx->stream>>>(ctx->d_ends, ctx->d_sweep, ctx->d_sweep_prefix,
-                                                   ctx->n_sweep, ctx->n_sweep_items, ctx->bin.sx,
-                                                   ctx->bin.sy, ctx->g.nx, rank, world, ctx->peer_ends);
-    GV_LAUNCH_CHECK();
-  }
-  k_sweep_compact<<<nb, kThreads, 0, ctx->stream>>>(ctx->d_ends, ctx->d_hit, ctx->d_miss, ctx->d_sweep,
-                                                    ctx->d_sweep_prefix, ctx->n_sweep,
-                                                    ctx->n_sweep_items, ctx->bin.sx, ctx->bin.sy,
-                                                    ctx->g.nx, rank, world, world == 1 ? 1 : 0,
-                                                    ctx->d_list_count, d_bentry, d_bmi, d_bw,
-                                                    ctx->d_stats);
+  stage_mark(ctx, 2);
+  if (p2p_gather)  // sums (and clears) the cells it owns in every rank's plane over NVLink
+    k_sweep_compact<true><<<nb, kThreads, 0, ctx->stream>>>(
+      ctx->d_ends, ctx->d_hit, ctx->d_miss, ctx->d_sweep, ctx->d_sweep_prefix, ctx->n_sweep, ctx->n_sweep_items,
+      ctx->bin.sx, ctx->bin.sy, ctx->g.nx, rank, world, 1, ctx->d_list_count, d_bentry, d_bmi, d_bw, ctx->d_stats,
+      ctx->peer_ends_buf[ctx->ends_cur]);
+  else
+    k_sweep_compact<false><<<nb, kThreads, 0, ctx->stream>>>(
+      ctx->d_ends, ctx->d_hit, ctx->d_miss, ctx->d_sweep, ctx->d_sweep_prefix, ctx->n_sweep, ctx->n_sweep_items,
+      ctx->bin.sx, ctx->bin.sy, ctx->g.nx, rank, world, world == 1 ? 1 : 0, ctx->d_list_count, d_bentry, d_bmi,
+      d_bw, ctx->d_stats, ctx->peer_ends);
   GV_LAUNCH_CHECK();
+  stage_mark(ctx, 3);
   k_sweep_walk<<<nb, kThreads, 0, ctx->stream>>>(ctx->d_miss, ctx->d_sweep, ctx->d_list_count, d_bentry,
                                                  d_bmi, d_bw, ctx->bin.sx, ctx->bin.sy, ctx->g.nx,
                                                  ctx->d_stats);
   GV_LAUNCH_CHECK();
+  stage_mark(ctx, 4);
   // multi-GPU, NCCL path: the plane holds every rank's (all-reduced) entries but this rank
-  // walked only its own items: drop the rest.  In P2P mode the peers may still be gathering
-  // from this plane: the caller clears it after the next barrier instead.
+  // walked only its own items: drop the rest.  (P2P: the owners cleared every rank's cells.)
   if (world > 1 && !p2p_gather)
     GV_CUDA(cudaMemsetAsync(ctx->d_ends, 0, ctx->ncells * sizeof(unsigned long long), ctx->stream));
   ctx->counts_dirty = true;
@@ -619,13 +706,18 @@ void close_peers(gv_ctx *ctx)
   if (!ctx->p2p) return;
   for (int r = 0; r < ctx->world && r < kMaxPeers; ++r) {
     if (r == ctx->rank) continue;
-    if (ctx->peer_ends.p[r]) cudaIpcCloseMemHandle(ctx->peer_ends.p[r]);
+    if (ctx->peer_ends_buf[0].p[r]) cudaIpcCloseMemHandle(ctx->peer_ends_buf[0].p[r]);
+    if (ctx->peer_ends_buf[1].p[r]) cudaIpcCloseMemHandle(ctx->peer_ends_buf[1].p[r]);
+    if (ctx->peer_flags.p[r]) cudaIpcCloseMemHandle(ctx->peer_flags.p[r]);
     if (ctx->peer_hit.p[r]) cudaIpcCloseMemHandle(ctx->peer_hit.p[r]);
     if (ctx->peer_miss.p[r]) cudaIpcCloseMemHandle(ctx->peer_miss.p[r]);
     if (ctx->peer_lo.p[r]) cudaIpcCloseMemHandle(ctx->peer_lo.p[r]);
     if (ctx->peer_occ.p[r]) cudaIpcCloseMemHandle(ctx->peer_occ.p[r]);
   }
   ctx->peer_ends = {};
+  ctx->peer_ends_buf[0] = {};
+  ctx->peer_ends_buf[1] = {};
+  ctx->peer_flags = {};
   ctx->peer_hit = {};
   ctx->peer_miss = {};
   ctx->peer_lo = {};
@@ -641,7 +733,9 @@ void free_grid(gv_ctx *ctx)
   cudaFree(ctx->d_occ);
   cudaFree(ctx->d_hit);
   cudaFree(ctx->d_miss);
-  cudaFree(ctx->d_ends);
+  cudaFree(ctx->d_ends_buf[0]);
+  cudaFree(ctx->d_ends_buf[1]);
+  ctx->d_ends_buf[0] = ctx->d_ends_buf[1] = nullptr;
   ctx->d_lo = ctx->d_occ = nullptr;
   ctx->d_hit = ctx->d_miss = nullptr;
   ctx->d_ends = nullptr;
@@ -702,6 +796,7 @@ int grid_init_impl(gv_ctx *ctx, double length_x, double length_y, double res, do
   const double sx = std::round(length_x / res), sy = std::round(length_y / res);
   GV_REQUIRE(sx >= 1.0 && sy >= 1.0 && sx * sy <= 2147483647.0, GV_ERR_INVALID,
              "grid of %.0f x %.0f cells unsupported", sx, sy);
+  GV_TRY(join_merge(ctx));
   GV_CUDA(cudaStreamSynchronize(ctx->stream));
   free_grid(ctx);
   GridGeom &g = ctx->g;
@@ -720,13 +815,17 @@ int grid_init_impl(gv_ctx *ctx, double length_x, double length_y, double res, do
   GV_CUDA(cudaMalloc(&ctx->d_occ, padded * sizeof(float)));
   GV_CUDA(cudaMalloc(&ctx->d_hit, padded * sizeof(int32_t)));
   GV_CUDA(cudaMalloc(&ctx->d_miss, padded * sizeof(int32_t)));
-  GV_CUDA(cudaMalloc(&ctx->d_ends, padded * sizeof(unsigned long long)));
+  GV_CUDA(cudaMalloc(&ctx->d_ends_buf[0], padded * sizeof(unsigned long long)));
+  GV_CUDA(cudaMalloc(&ctx->d_ends_buf[1], padded * sizeof(unsigned long long)));
+  ctx->ends_cur = 0;
+  ctx->d_ends = ctx->d_ends_buf[0];
   ctx->has_grid = true;
   GV_CUDA(cudaMemsetAsync(ctx->d_lo, 0, padded * sizeof(float), ctx->stream));
   GV_CUDA(cudaMemsetAsync(ctx->d_occ, 0, padded * sizeof(float), ctx->stream));
   GV_CUDA(cudaMemsetAsync(ctx->d_hit, 0, padded * sizeof(int32_t), ctx->stream));
   GV_CUDA(cudaMemsetAsync(ctx->d_miss, 0, padded * sizeof(int32_t), ctx->stream));
-  GV_CUDA(cudaMemsetAsync(ctx->d_ends, 0, padded * sizeof(unsigned long long), ctx->stream));
+  GV_CUDA(cudaMemsetAsync(ctx->d_ends_buf[0], 0, padded * sizeof(unsigned long long), ctx->stream));
+  GV_CUDA(cudaMemsetAsync(ctx->d_ends_buf[1], 0, padded * sizeof(unsigned long long), ctx->stream));
   // ref: src/occupancy_grid.cpp:12-13 log_odds = log_odds_prior_ (0.0f), occupancy = 0.5f
   k_fill_f32<<<ctx->num_sms * 4, kThreads, 0, ctx->stream>>>(ctx->d_occ, ctx->ncells, 0.5f);
   GV_LAUNCH_CHECK();
@@ -781,6 +880,12 @@ int gv_create(gv_ctx **out, int device)
       cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_bin_done, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_merge_done[0], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_merge_done[1], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreate(&ctx->ev_merge_t0) != cudaSuccess || cudaEventCreate(&ctx->ev_merge_t1) != cudaSuccess ||
+      cudaMalloc(&ctx->d_flags, (kMaxPeers + 1) * sizeof(unsigned)) != cudaSuccess ||
+      cudaMemset(ctx->d_flags, 0, (kMaxPeers + 1) * sizeof(unsigned)) != cudaSuccess ||
       cudaMalloc(&ctx->d_stats, 4 * sizeof(unsigned long long)) != cudaSuccess ||
       cudaMalloc(&ctx->d_list_count, 4 * sizeof(unsigned)) != cudaSuccess ||
       cudaMemset(ctx->d_stats, 0, 4 * sizeof(unsigned long long)) != cudaSuccess) {
@@ -789,6 +894,18 @@ int gv_create(gv_ctx **out, int device)
     return GV_ERR_CUDA;
   }
   ctx->stream = ctx->own_stream;
+  {
+    // the merge of batch i runs beside the binning of batch i+1: give it the higher priority so
+    // its (few, latency-bound) CTAs are placed as soon as resources free up
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&ctx->merge_stream, cudaStreamNonBlocking, hi) != cudaSuccess) {
+      cudaGetLastError();
+      gv_destroy(ctx);
+      return GV_ERR_CUDA;
+    }
+  }
+  if (const char *u = std::getenv("GV_OVERLAP")) ctx->overlap = std::atoi(u) != 0;
   ctx->timing = std::getenv("GV_TIMING") != nullptr;
   ctx->use_fast = std::getenv("GV_NO_FAST") == nullptr;
   if (const char *u = std::getenv("GV_FAST_U")) ctx->fast_unroll = std::atoi(u);
@@ -836,6 +953,13 @@ void gv_destroy(gv_ctx *ctx)
   cudaFree(ctx->d_list_count);
   cudaFree(ctx->d_barrier);
   for (auto e : ctx->events) cudaEventDestroy(e);
+  if (ctx->merge_stream) cudaStreamDestroy(ctx->merge_stream);
+  if (ctx->ev_bin_done) cudaEventDestroy(ctx->ev_bin_done);
+  for (auto e : ctx->ev_merge_done)
+    if (e) cudaEventDestroy(e);
+  if (ctx->ev_merge_t0) cudaEventDestroy(ctx->ev_merge_t0);
+  if (ctx->ev_merge_t1) cudaEventDestroy(ctx->ev_merge_t1);
+  cudaFree(ctx->d_flags);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
   if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
@@ -849,8 +973,16 @@ int gv_synchronize(gv_ctx *ctx)
 {
   if (!ctx) return GV_ERR_INVALID;
   GV_CUDA(cudaSetDevice(ctx->device));
+  GV_TRY(join_merge(ctx));
   GV_CUDA(cudaStreamSynchronize(ctx->stream));
-  return GV_OK;
+  return check_barrier_timeout(ctx);
+}
+
+int gv_join(gv_ctx *ctx)
+{
+  if (!ctx) return GV_ERR_INVALID;
+  GV_CUDA(cudaSetDevice(ctx->device));
+  return join_merge(ctx);
 }
 
 void *gv_stream(gv_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
@@ -858,6 +990,7 @@ void *gv_stream(gv_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 int gv_set_stream(gv_ctx *ctx, void *stream)
 {
   if (!ctx) return GV_ERR_INVALID;
+  GV_TRY(join_merge(ctx));
   GV_CUDA(cudaStreamSynchronize(ctx->stream));
   // the handle is used as given: NULL is the legacy default stream (torch's default current
   // stream), not "reset"; gv_stream() of a fresh context returns its private stream
@@ -868,9 +1001,17 @@ int gv_set_stream(gv_ctx *ctx, void *stream)
 int gv_get_stats(gv_ctx *ctx, gv_stats *out)
 {
   if (!ctx || !out) return GV_ERR_INVALID;
+  GV_TRY(join_merge(ctx));
   unsigned long long h[4];
   GV_CUDA(cudaMemcpyAsync(h, ctx->d_stats, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
   GV_CUDA(cudaStreamSynchronize(ctx->stream));
+  out->merges = ctx->merges;
+  out->merge_ms_last = 0.0;
+  if (ctx->merge_timed) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev_merge_t0, ctx->ev_merge_t1) == cudaSuccess) out->merge_ms_last = ms;
+    cudaGetLastError();
+  }
   out->beams = h[0];
   out->cells_logical = h[1];
   out->cells_physical = h[2];
@@ -1294,11 +1435,13 @@ int gv_grid_reset(gv_ctx *ctx)
   if (!ctx) return GV_ERR_INVALID;
   GV_CUDA(cudaSetDevice(ctx->device));
   GV_REQUIRE(ctx->has_grid, GV_ERR_STATE, "grid not initialised");
+  GV_TRY(join_merge(ctx));
   const size_t padded = ctx->ncells + kPlanePad;
   GV_CUDA(cudaMemsetAsync(ctx->d_lo, 0, padded * sizeof(float), ctx->stream));
   GV_CUDA(cudaMemsetAsync(ctx->d_hit, 0, padded * sizeof(int32_t), ctx->stream));
   GV_CUDA(cudaMemsetAsync(ctx->d_miss, 0, padded * sizeof(int32_t), ctx->stream));
-  GV_CUDA(cudaMemsetAsync(ctx->d_ends, 0, padded * sizeof(unsigned long long), ctx->stream));
+  GV_CUDA(cudaMemsetAsync(ctx->d_ends_buf[0], 0, padded * sizeof(unsigned long long), ctx->stream));
+  GV_CUDA(cudaMemsetAsync(ctx->d_ends_buf[1], 0, padded * sizeof(unsigned long long), ctx->stream));
   k_fill_f32<<<ctx->num_sms * 4, kThreads, 0, ctx->stream>>>(ctx->d_occ, ctx->ncells, 0.5f);
   GV_LAUNCH_CHECK();
   GV_CUDA(cudaMemsetAsync(ctx->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
@@ -1312,6 +1455,7 @@ int gv_grid_upload(gv_ctx *ctx, const float *log_odds, const float *occupancy)
   if (!ctx) return GV_ERR_INVALID;
   GV_CUDA(cudaSetDevice(ctx->device));
   GV_REQUIRE(ctx->has_grid, GV_ERR_STATE, "grid not initialised");
+  GV_TRY(join_merge(ctx));
   const size_t bytes = ctx->ncells * sizeof(float);
   if (log_odds)
     GV_CUDA(cudaMemcpyAsync(ctx->d_lo, log_odds, bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -1326,6 +1470,7 @@ int gv_grid_download(gv_ctx *ctx, float *log_odds, float *occupancy)
   if (!ctx) return GV_ERR_INVALID;
   GV_CUDA(cudaSetDevice(ctx->device));
   GV_REQUIRE(ctx->has_grid, GV_ERR_STATE, "grid not initialised");
+  GV_TRY(join_merge(ctx));
   const size_t bytes = ctx->ncells * sizeof(float);
   if (log_odds)
     GV_CUDA(cudaMemcpyAsync(log_odds, ctx->d_lo, bytes, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1340,6 +1485,7 @@ int gv_grid_counts_download(gv_ctx *ctx, int32_t *hit, int32_t *miss)
   if (!ctx) return GV_ERR_INVALID;
   GV_CUDA(cudaSetDevice(ctx->device));
   GV_REQUIRE(ctx->has_grid, GV_ERR_STATE, "grid not initialised");
+  GV_TRY(join_merge(ctx));
   GV_TRY(raycast_flush_impl(ctx, 0, 1));
   const size_t bytes = ctx->ncells * sizeof(int32_t);
   if (hit) GV_CUDA(cudaMemcpyAsync(hit, ctx->d_hit, bytes, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1353,6 +1499,7 @@ int gv_grid_layers_dev(gv_ctx *ctx, float **d_log_odds, float **d_occupancy, int
 {
   if (!ctx) return GV_ERR_INVALID;
   GV_REQUIRE(ctx->has_grid, GV_ERR_STATE, "grid not initialised");
+  GV_TRY(join_merge(ctx));
   if (d_log_odds) *d_log_odds = ctx->d_lo;
   if (d_occupancy) *d_occupancy = ctx->d_occ;
   if (d_hit) *d_hit = ctx->d_hit;
@@ -1365,6 +1512,7 @@ int gv_grid_get_index(gv_ctx *ctx, const double *xy, int n, int32_t *ixy_out)
   if (!ctx) return GV_ERR_INVALID;
   GV_CUDA(cudaSetDevice(ctx->device));
   GV_REQUIRE(ctx->has_grid, GV_ERR_STATE, "grid not initialised");
+  GV_TRY(join_merge(ctx));
   if (n <= 0) return GV_OK;
   GV_REQUIRE(xy && ixy_out, GV_ERR_INVALID, "xy / ixy_out is NULL");
   double *d_in;
@@ -1388,6 +1536,7 @@ int gv_grid_update(gv_ctx *ctx)
 {
   if (!ctx) return GV_ERR_INVALID;
   GV_CUDA(cudaSetDevice(ctx->device));
+  GV_TRY(join_merge(ctx));
   return finalize_impl(ctx, 1, nullptr, nullptr, 0, 0);
 }
 
@@ -1395,6 +1544,7 @@ int gv_grid_update_poses(gv_ctx *ctx, const double *xylw, int n)
 {
   if (!ctx) return GV_ERR_INVALID;
   GV_CUDA(cudaSetDevice(ctx->device));
+  GV_TRY(join_merge(ctx));
   return finalize_impl(ctx, 1, xylw, nullptr, n, 1);
 }
 
@@ -1402,6 +1552,7 @@ int gv_grid_update_points(gv_ctx *ctx, const double *xy, const int32_t *labels, 
 {
   if (!ctx) return GV_ERR_INVALID;
   GV_CUDA(cudaSetDevice(ctx->device));
+  GV_TRY(join_merge(ctx));
   return finalize_impl(ctx, 1, xy, labels, n, 2);
 }
 
@@ -1409,6 +1560,7 @@ int gv_grid_update_corners(gv_ctx *ctx, const double *corners, int n)
 {
   if (!ctx) return GV_ERR_INVALID;
   GV_CUDA(cudaSetDevice(ctx->device));
+  GV_TRY(join_merge(ctx));
   return finalize_impl(ctx, 1, corners, nullptr, n, 0);
 }
 
@@ -1420,6 +1572,7 @@ int gv_set_base_transform(gv_ctx *ctx, const float *T_base_lidar)
   if (!ctx) return GV_ERR_INVALID;
   GV_CUDA(cudaSetDevice(ctx->device));
   GV_REQUIRE(T_base_lidar != nullptr, GV_ERR_INVALID, "T_base_lidar is NULL");
+  GV_TRY(join_merge(ctx));
   // beams binned under the previous pose belong to the previous start cell: walk them first
   if (ctx->has_grid && ctx->ends_dirty) GV_TRY(raycast_flush_impl(ctx, 0, 1));
   memcpy(ctx->Tb, T_base_lidar, sizeof(ctx->Tb));
@@ -1471,6 +1624,7 @@ int gv_grid_raycast_flush(gv_ctx *ctx)
   if (!ctx) return GV_ERR_INVALID;
   GV_CUDA(cudaSetDevice(ctx->device));
   GV_REQUIRE(ctx->has_grid, GV_ERR_STATE, "grid not initialised");
+  GV_TRY(join_merge(ctx));
   return raycast_flush_impl(ctx, 0, 1);
 }
 
@@ -1478,7 +1632,10 @@ int gv_grid_finalize(gv_ctx *ctx, int32_t k_decay, const double *corners, int nf
 {
   if (!ctx) return GV_ERR_INVALID;
   GV_CUDA(cudaSetDevice(ctx->device));
-  return finalize_impl(ctx, k_decay, corners, nullptr, nfoot, 0);
+  GV_REQUIRE(ctx->has_grid, GV_ERR_STATE, "grid not initialised");
+  MergeScope sc;
+  GV_TRY(merge_begin(ctx, &sc));
+  return merge_end(ctx, &sc, finalize_impl(ctx, k_decay, corners, nullptr, nfoot, 0));
 }
 
 // Persisting-L2 access window on the end-cell plane for the kernels launched next on the context
@@ -1742,6 +1899,7 @@ static int process_batch_impl(gv_ctx *ctx, const float *px, const float *py, con
   memset(&a, 0, sizeof(a));
   GV_TRY(set_bin_params(ctx, prm, &a.bin));
   GV_TRY(note_beams(ctx, n));
+  GV_TRY(bin_begin(ctx));
 
   // points: device-resident, or staged per chunk from host memory
   const uint64_t base = points_on_device ? 0 : p0;  // host path rebases the staged copy to 0
@@ -2009,6 +2167,7 @@ int gv_grid_to_occupancy(gv_ctx *ctx, int8_t *data_out)
   if (!ctx) return GV_ERR_INVALID;
   GV_CUDA(cudaSetDevice(ctx->device));
   GV_REQUIRE(ctx->has_grid, GV_ERR_STATE, "grid not initialised");
+  GV_TRY(join_merge(ctx));
   GV_REQUIRE(data_out != nullptr, GV_ERR_INVALID, "data_out is NULL");
   int8_t *d_out;
   GV_TRY(reserve_t(ctx, S_FLAGS, ctx->ncells, &d_out));
@@ -2103,62 +2262,59 @@ static int check_ranks_agree(gv_ctx *ctx)
 }
 #endif
 
-int gv_grid_finalize_multi(gv_ctx *ctx, int32_t k_decay, const double *corners, int nfoot)
-{
-  if (!ctx) return GV_ERR_INVALID;
-  GV_CUDA(cudaSetDevice(ctx->device));
-  GV_REQUIRE(ctx->has_grid, GV_ERR_STATE, "grid not initialised");
 #ifdef GV_WITH_NCCL
-  if (ctx->world == 1 || ctx->comm == nullptr) return finalize_impl(ctx, k_decay, corners, nullptr, nfoot, 0);
+static int finalize_multi_chain(gv_ctx *ctx, int32_t k_decay, const double *corners, int nfoot)
+{
   const unsigned world = (unsigned)ctx->world, rank = (unsigned)ctx->rank;
-  GV_TRY(check_ranks_agree(ctx));
   // equal slabs, 4-cell aligned (k_finalize vector width); planes carry kPlanePad slack cells
   size_t slab = (ctx->ncells + world - 1) / world;
   slab = (slab + 3) & ~(size_t)3;
   GV_REQUIRE(slab * world <= ctx->ncells + kPlanePad, GV_ERR_INVALID, "grid too small for %u ranks", world);
+  const size_t c0 = (size_t)rank * slab;
+  const size_t c1 = c0 + slab < ctx->ncells ? c0 + slab : ctx->ncells;
   if (ctx->p2p) {
-    // ---- fused over peer memory (NVLink P2P): NCCL only for one-word stream barriers
-    if (!ctx->d_barrier) {
-      GV_CUDA(cudaMalloc(&ctx->d_barrier, sizeof(int)));
-      GV_CUDA(cudaMemsetAsync(ctx->d_barrier, 0, sizeof(int), ctx->stream));
-    }
+    // ---- fused over peer memory (NVLink P2P).  Barriers are k_peer_barrier launches (flag words
+    // in peer memory), no NCCL call on this path.
     auto barrier = [&]() -> int {
-      GV_NCCL(ncclAllReduce(ctx->d_barrier, ctx->d_barrier, 1, ncclInt32, ncclSum, ctx->comm, ctx->stream));
+      ctx->barrier_epoch++;
+      k_peer_barrier<<<1, 32, 0, ctx->stream>>>(ctx->peer_flags, rank, world, ctx->barrier_epoch,
+                                                ctx->d_flags + kMaxPeers);
+      GV_LAUNCH_CHECK();
       return GV_OK;
     };
     stage_mark(ctx, 0);
-    GV_TRY(barrier());  // every rank has finished binning into its ends plane
+    GV_TRY(barrier());  // every rank has finished binning into its current end-cell plane
     stage_mark(ctx, 1);
-    ctx->ends_dirty = true;
-    GV_TRY(raycast_flush_impl(ctx, rank, world, true));  // gathers its cells from all ranks, walks
-    stage_mark(ctx, 2);
-    GV_TRY(barrier());  // every rank's partial hit/miss planes are complete, gathers are done
-    GV_CUDA(cudaMemsetAsync(ctx->d_ends, 0, ctx->ncells * sizeof(unsigned long long), ctx->stream));
-    stage_mark(ctx, 3);
+    ctx->ends_dirty = true;  // a rank with no local beams still owns a share of the lines
+    // sweep: sums + clears the cells of its spans in every rank's plane, walks its lines
+    GV_TRY(raycast_flush_impl(ctx, rank, world, true));
+    stage_mark(ctx, 5);
+    GV_TRY(barrier());  // every rank's partial hit/miss planes are complete
+    stage_mark(ctx, 6);
     int4 *d_rects = nullptr;
     GV_TRY(footprint_rects(ctx, corners, nullptr, nfoot, 0, &d_rects));
-    const size_t c0 = (size_t)rank * slab;
-    const size_t c1 = c0 + slab < ctx->ncells ? c0 + slab : ctx->ncells;
+    // slab owner: sums all ranks' counts (reduce-scatter), finalises, writes every rank's grid (all-gather)
     if (c1 > c0) GV_TRY(finalize_slab(ctx, k_decay, d_rects, nfoot, c0, c1 - c0, true, true));
-    stage_mark(ctx, 4);
-    GV_TRY(barrier());  // every slab has been written into every rank's grid, counts consumed
+    stage_mark(ctx, 7);
+    GV_TRY(barrier());  // every slab is in every rank's grid; all count reads are done
     GV_CUDA(cudaMemsetAsync(ctx->d_hit, 0, ctx->ncells * sizeof(int32_t), ctx->stream));
     GV_CUDA(cudaMemsetAsync(ctx->d_miss, 0, ctx->ncells * sizeof(int32_t), ctx->stream));
-    stage_mark(ctx, 5);
+    stage_mark(ctx, 8);
     stage_collect(ctx);
     ctx->counts_dirty = false;
     ctx->beams_bound = 0;
     return GV_OK;
   }
+  // ---- NCCL collectives
   // 1. every rank learns every rank's binned beams: exact u64 sum of the (total,hit) plane
   stage_mark(ctx, 0);
   GV_NCCL(ncclAllReduce(ctx->d_ends, ctx->d_ends, ctx->ncells, ncclUint64, ncclSum, ctx->comm,
                         ctx->stream));
-  // 2. the de-duplicated raycast is split by end cell (lin % world), partial planes result
+  // 2. the de-duplicated raycast is split by span, partial planes result
   stage_mark(ctx, 1);
   ctx->ends_dirty = true;  // a rank with no local beams still owns a share of the lines
   GV_TRY(raycast_flush_impl(ctx, rank, world));
-  stage_mark(ctx, 2);
+  stage_mark(ctx, 5);
   // 3. exact int32 sums of the partial planes, scattered by slab
   GV_NCCL(ncclGroupStart());
   GV_NCCL(ncclReduceScatter(ctx->d_hit, ctx->d_hit + (size_t)rank * slab, slab, ncclInt32, ncclSum,
@@ -2166,29 +2322,41 @@ int gv_grid_finalize_multi(gv_ctx *ctx, int32_t k_decay, const double *corners, 
   GV_NCCL(ncclReduceScatter(ctx->d_miss, ctx->d_miss + (size_t)rank * slab, slab, ncclInt32,
                             ncclSum, ctx->comm, ctx->stream));
   GV_NCCL(ncclGroupEnd());
-  stage_mark(ctx, 3);
+  stage_mark(ctx, 6);
   // 4. finalise the local slab
   int4 *d_rects = nullptr;
   GV_TRY(footprint_rects(ctx, corners, nullptr, nfoot, 0, &d_rects));
-  const size_t c0 = (size_t)rank * slab;
-  const size_t c1 = c0 + slab < ctx->ncells ? c0 + slab : ctx->ncells;
   if (c1 > c0) GV_TRY(finalize_slab(ctx, k_decay, d_rects, nfoot, c0, c1 - c0, true));
   const size_t padded = ctx->ncells + kPlanePad;
   GV_CUDA(cudaMemsetAsync(ctx->d_hit, 0, padded * sizeof(int32_t), ctx->stream));
   GV_CUDA(cudaMemsetAsync(ctx->d_miss, 0, padded * sizeof(int32_t), ctx->stream));
-  stage_mark(ctx, 4);
+  stage_mark(ctx, 7);
   // 5. every rank ends with the full grid
   GV_NCCL(ncclGroupStart());
   GV_NCCL(ncclAllGather(ctx->d_lo + c0, ctx->d_lo, slab, ncclFloat32, ctx->comm, ctx->stream));
   GV_NCCL(ncclAllGather(ctx->d_occ + c0, ctx->d_occ, slab, ncclFloat32, ctx->comm, ctx->stream));
   GV_NCCL(ncclGroupEnd());
-  stage_mark(ctx, 5);
+  stage_mark(ctx, 8);
   stage_collect(ctx);
   ctx->counts_dirty = false;
   ctx->beams_bound = 0;
   return GV_OK;
+}
+#endif
+
+int gv_grid_finalize_multi(gv_ctx *ctx, int32_t k_decay, const double *corners, int nfoot)
+{
+  if (!ctx) return GV_ERR_INVALID;
+  GV_CUDA(cudaSetDevice(ctx->device));
+  GV_REQUIRE(ctx->has_grid, GV_ERR_STATE, "grid not initialised");
+#ifdef GV_WITH_NCCL
+  if (ctx->world == 1 || ctx->comm == nullptr) return gv_grid_finalize(ctx, k_decay, corners, nfoot);
+  GV_TRY(check_ranks_agree(ctx));
+  MergeScope sc;
+  GV_TRY(merge_begin(ctx, &sc));
+  return merge_end(ctx, &sc, finalize_multi_chain(ctx, k_decay, corners, nfoot));
 #else
-  if (ctx->world == 1) return finalize_impl(ctx, k_decay, corners, nullptr, nfoot, 0);
+  if (ctx->world == 1) return gv_grid_finalize(ctx, k_decay, corners, nfoot);
   return ctx->fail(GV_ERR_NCCL, "library built without NCCL");
 #endif
 }
@@ -2199,13 +2367,15 @@ int gv_ipc_export(gv_ctx *ctx, void *blob_out)
   GV_CUDA(cudaSetDevice(ctx->device));
   GV_REQUIRE(ctx->has_grid, GV_ERR_STATE, "grid not initialised");
   GV_REQUIRE(blob_out != nullptr, GV_ERR_INVALID, "blob_out is NULL");
-  static_assert(5 * sizeof(cudaIpcMemHandle_t) == GV_IPC_BLOB_BYTES, "ipc blob size");
-  cudaIpcMemHandle_t h[5];
-  GV_CUDA(cudaIpcGetMemHandle(&h[0], ctx->d_ends));
-  GV_CUDA(cudaIpcGetMemHandle(&h[1], ctx->d_hit));
-  GV_CUDA(cudaIpcGetMemHandle(&h[2], ctx->d_miss));
-  GV_CUDA(cudaIpcGetMemHandle(&h[3], ctx->d_lo));
-  GV_CUDA(cudaIpcGetMemHandle(&h[4], ctx->d_occ));
+  static_assert(7 * sizeof(cudaIpcMemHandle_t) == GV_IPC_BLOB_BYTES, "ipc blob size");
+  cudaIpcMemHandle_t h[7];
+  GV_CUDA(cudaIpcGetMemHandle(&h[0], ctx->d_ends_buf[0]));
+  GV_CUDA(cudaIpcGetMemHandle(&h[1], ctx->d_ends_buf[1]));
+  GV_CUDA(cudaIpcGetMemHandle(&h[2], ctx->d_hit));
+  GV_CUDA(cudaIpcGetMemHandle(&h[3], ctx->d_miss));
+  GV_CUDA(cudaIpcGetMemHandle(&h[4], ctx->d_lo));
+  GV_CUDA(cudaIpcGetMemHandle(&h[5], ctx->d_occ));
+  GV_CUDA(cudaIpcGetMemHandle(&h[6], ctx->d_flags));
   memcpy(blob_out, h, sizeof(h));
   return GV_OK;
 }
@@ -2218,23 +2388,26 @@ int gv_ipc_import(gv_ctx *ctx, const void *blobs, int world, int rank)
   GV_REQUIRE(blobs && world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, GV_ERR_INVALID,
              "bad rank/world %d/%d (at most %d peers)", rank, world, kMaxPeers);
   GV_REQUIRE(world == ctx->world && rank == ctx->rank, GV_ERR_STATE,
-             "gv_nccl_init must come first (barriers) and agree on rank/world");
+             "gv_nccl_init must come first and agree on rank/world");
+  GV_TRY(join_merge(ctx));
   GV_CUDA(cudaStreamSynchronize(ctx->stream));
   close_peers(ctx);
   ctx->p2p = true;  // so that close_peers cleans up a partial import
   for (int r = 0; r < world; ++r) {
     if (r == rank) {
-      ctx->peer_ends.p[r] = ctx->d_ends;
+      ctx->peer_ends_buf[0].p[r] = ctx->d_ends_buf[0];
+      ctx->peer_ends_buf[1].p[r] = ctx->d_ends_buf[1];
       ctx->peer_hit.p[r] = ctx->d_hit;
       ctx->peer_miss.p[r] = ctx->d_miss;
       ctx->peer_lo.p[r] = ctx->d_lo;
       ctx->peer_occ.p[r] = ctx->d_occ;
+      ctx->peer_flags.p[r] = ctx->d_flags;
       continue;
     }
-    cudaIpcMemHandle_t h[5];
+    cudaIpcMemHandle_t h[7];
     memcpy(h, static_cast<const char *>(blobs) + (size_t)r * GV_IPC_BLOB_BYTES, sizeof(h));
-    void *q[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    for (int k = 0; k < 5; ++k) {
+    void *q[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    for (int k = 0; k < 7; ++k) {
       const cudaError_t e = cudaIpcOpenMemHandle(&q[k], h[k], cudaIpcMemLazyEnablePeerAccess);
       if (e != cudaSuccess) {
         cudaGetLastError();
@@ -2244,12 +2417,18 @@ int gv_ipc_import(gv_ctx *ctx, const void *blobs, int world, int rank)
                          cudaGetErrorString(e));
       }
     }
-    ctx->peer_ends.p[r] = static_cast<unsigned long long *>(q[0]);
-    ctx->peer_hit.p[r] = static_cast<int32_t *>(q[1]);
-    ctx->peer_miss.p[r] = static_cast<int32_t *>(q[2]);
-    ctx->peer_lo.p[r] = static_cast<float *>(q[3]);
-    ctx->peer_occ.p[r] = static_cast<float *>(q[4]);
+    ctx->peer_ends_buf[0].p[r] = static_cast<unsigned long long *>(q[0]);
+    ctx->peer_ends_buf[1].p[r] = static_cast<unsigned long long *>(q[1]);
+    ctx->peer_hit.p[r] = static_cast<int32_t *>(q[2]);
+    ctx->peer_miss.p[r] = static_cast<int32_t *>(q[3]);
+    ctx->peer_lo.p[r] = static_cast<float *>(q[4]);
+    ctx->peer_occ.p[r] = static_cast<float *>(q[5]);
+    ctx->peer_flags.p[r] = static_cast<unsigned *>(q[6]);
   }
+  ctx->peer_ends = ctx->peer_ends_buf[ctx->ends_cur];
+  // the barrier epochs of all ranks restart together
+  ctx->barrier_epoch = 0;
+  GV_CUDA(cudaMemset(ctx->d_flags, 0, (kMaxPeers + 1) * sizeof(unsigned)));
   return GV_OK;
 }
 
@@ -2257,6 +2436,7 @@ int gv_ipc_close(gv_ctx *ctx)
 {
   if (!ctx) return GV_ERR_INVALID;
   GV_CUDA(cudaSetDevice(ctx->device));
+  GV_TRY(join_merge(ctx));
   GV_CUDA(cudaStreamSynchronize(ctx->stream));
   close_peers(ctx);
   return GV_OK;

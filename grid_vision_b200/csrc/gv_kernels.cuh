@@ -860,13 +860,18 @@ constexpr int kSpanCells = 32 * kSpanChunks;
 // One CTA per span: 8 warps x 4 chunks, four independent loads per thread, a block prefix over
 // the per-chunk ballots, one atomic per span to reserve its batches.  (A warp-per-span version
 // spent ~0.1 ms in 64 dependent loads per warp whatever the rank's share of the spans.)
+// P2P (multi-GPU over peer memory): the entries of a cell are summed over EVERY rank's plane with
+// NVLink loads and every rank's cell is cleared with NVLink stores, right here: span ownership
+// partitions the cells, so this CTA is the only reader of these cells on any rank.  This is the
+// all-reduce of the end-cell planes, restricted to what this rank walks, fused into the sweep.
+template <bool P2P>
 __global__ void __launch_bounds__(kThreads) k_sweep_compact(
   unsigned long long *__restrict__ ends, int32_t *__restrict__ hit, int32_t *__restrict__ miss,
   const SweepEntry *__restrict__ entries, const unsigned *__restrict__ item_prefix, int n_entries,
   unsigned n_items, int sx, int sy, int nx, unsigned rank, unsigned world, int clear_ends,
   unsigned *__restrict__ counters /* [0] item counter, [1] batch count */,
   int *__restrict__ batch_entry, int *__restrict__ batch_mi, unsigned *__restrict__ batch_w,
-  unsigned long long *__restrict__ stats)
+  unsigned long long *__restrict__ stats, const __grid_constant__ Peers<unsigned long long> peer_ends)
 {
   constexpr int kWarps = kThreads / 32;
   constexpr int kPer = kSpanChunks / kWarps;  // chunks per warp
@@ -895,7 +900,16 @@ __global__ void __launch_bounds__(kThreads) k_sweep_compact(
       mi[j] = span0 + ((int)wid * kPer + j) * 32 + (int)lane;
       int ex, ey;
       elin[j] = sweep_end_cell(E, mi[j] <= E.m1 ? mi[j] : E.m1, sx, sy, nx, ex, ey);
-      e[j] = mi[j] <= E.m1 ? ends[elin[j]] : 0ull;
+      e[j] = 0ull;
+      if (mi[j] <= E.m1) {
+        if (P2P) {
+#pragma unroll
+          for (int r = 0; r < kMaxPeers; ++r)
+            if (r < (int)world) e[j] += peer_ends.p[r][elin[j]];
+        } else {
+          e[j] = ends[elin[j]];
+        }
+      }
     }
     unsigned nz[kPer];
 #pragma unroll
@@ -929,7 +943,13 @@ __global__ void __launch_bounds__(kThreads) k_sweep_compact(
           batch_mi[o] = mi[j];
           batch_w[o] = w;
         }
-        if (clear_ends) ends[elin[j]] = 0ull;     // single GPU: this thread is the only reader of the cell
+        if (P2P) {
+#pragma unroll
+          for (int r = 0; r < kMaxPeers; ++r)
+            if (r < (int)world) peer_ends.p[r][elin[j]] = 0ull;  // this thread is the cell's only reader anywhere
+        } else if (clear_ends) {
+          ends[elin[j]] = 0ull;  // single GPU: this thread is the only reader of the cell
+        }
         if (hits) hit[elin[j]] += (int32_t)hits;  // only this thread ever writes hit[elin] in this kernel
         if (w - hits) atomicAdd(miss + elin[j], (int32_t)(w - hits));  // other lines pass through it
         st_beams += w;
@@ -1026,39 +1046,32 @@ __global__ void __launch_bounds__(kThreads) k_sweep_walk(
   if (lane == 0 && st_physical) atomicAdd(stats + 2, st_physical);
 }
 
-// Peer-memory gather (gv_grid_finalize_multi, P2P mode): for every item this rank owns, sum the
-// end-cell entries of ALL ranks' planes with NVLink loads into the local plane — the all-reduce
-// of the ends plane restricted to the cells whose lines this rank will walk.  Ownership
-// partitions the cells, so the local stores never touch a cell a peer is reading.
-__global__ void __launch_bounds__(kThreads) k_ends_gather(
-  unsigned long long *__restrict__ ends, const SweepEntry *__restrict__ entries,
-  const unsigned *__restrict__ item_prefix, int n_entries, unsigned n_items, int sx, int sy, int nx,
-  unsigned rank, unsigned world, const __grid_constant__ Peers<unsigned long long> peer_ends)
+// Stream-ordered barrier between the ranks of one node over peer memory: every rank owns a flag
+// word per peer (cudaIpc-mapped everywhere).  Rank r publishes `epoch` into slot r of every rank's
+// array, then waits until every slot of its own array has reached `epoch`.  One kernel per rank
+// per GPU (never two ranks on one GPU: a spinning kernel must not depend on a kernel that may not
+// be resident).  A rank that never arrives would hang the others, so the spin gives up after
+// ~2 s and raises *timeout_flag, which the host reports at the next synchronising call.
+__global__ void k_peer_barrier(const __grid_constant__ Peers<unsigned> flags, unsigned rank, unsigned world,
+                               unsigned epoch, unsigned *timeout_flag)
 {
-  const unsigned lane = threadIdx.x & 31;
-  const unsigned nwarps = gridDim.x * (blockDim.x >> 5);
-  for (unsigned long long t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);; t += nwarps) {
-    const unsigned long long item64 = t * world + rank;  // the items this rank's sweep will walk
-    if (item64 >= n_items) break;
-    const unsigned item = (unsigned)item64;
-    const int ei = sweep_find_entry(item_prefix, n_entries, item);
-    const SweepEntry E = entries[ei];
-    const int span0 = E.m0 + (int)(item - item_prefix[ei]) * kSpanCells;
-#pragma unroll 1
-    for (int c = 0; c < kSpanChunks; ++c) {
-      const int mi = span0 + c * 32 + (int)lane;
-      if (mi > E.m1) break;
-      int ex, ey;
-      const size_t elin = sweep_end_cell(E, mi, sx, sy, nx, ex, ey);
-      unsigned long long part[kMaxPeers];
-#pragma unroll
-      for (int r = 0; r < kMaxPeers; ++r) part[r] = r < (int)world ? peer_ends.p[r][elin] : 0ull;
-      unsigned long long e = 0ull;
-#pragma unroll
-      for (int r = 0; r < kMaxPeers; ++r) e += part[r];
-      ends[elin] = e;
+  const unsigned r = threadIdx.x;
+  if (r >= world) return;
+  __threadfence_system();  // this rank's earlier kernels' writes are visible before the arrival is
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flags.p[r] + rank), "r"(epoch) : "memory");
+  const unsigned *mine = flags.p[rank] + r;
+  const long long t0 = clock64();
+  for (;;) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+    if ((int)(v - epoch) >= 0) break;
+    if (clock64() - t0 > 4000000000ll) {
+      *timeout_flag = 1u;
+      break;
     }
+    __nanosleep(64);
   }
+  __threadfence_system();
 }
 
 // ----------------------------------------------------------------------------------

@@ -98,6 +98,8 @@ typedef struct {
   uint64_t cells_physical;    /* atomic cell updates actually issued after de-duplication */
   uint64_t distinct_ends;     /* (start,end) pairs walked                                 */
   uint64_t kernel_launches;   /* kernels launched by this context so far                  */
+  uint64_t merges;            /* gv_grid_finalize / _multi calls so far                    */
+  double merge_ms_last;       /* device time of the last one (raycast [+ exchange] + finalise) */
 } gv_stats;
 
 /* ------------------------------------------------------------------ lifecycle --- */
@@ -107,6 +109,13 @@ GV_API int gv_create(gv_ctx **out, int device);
 GV_API void gv_destroy(gv_ctx *ctx);
 GV_API const char *gv_last_error(const gv_ctx *ctx);
 GV_API int gv_synchronize(gv_ctx *ctx);
+/* gv_grid_finalize and gv_grid_finalize_multi return as soon as their work is queued: the merge
+ * of the batch binned so far (raycast, [exchange between ranks,] finalise) runs on an internal
+ * stream, ordered after the binning, while the caller's stream is free to bin the NEXT batch
+ * (gv_process_batch*, gv_grid_accumulate*) into a second end-cell plane.  Every entry point
+ * that reads or writes grid state waits for it by itself; gv_join makes the caller's stream
+ * wait explicitly (e.g. before recording a timing event).  $GV_OVERLAP=0 disables the overlap. */
+GV_API int gv_join(gv_ctx *ctx);
 GV_API void *gv_stream(gv_ctx *ctx);               /* cudaStream_t */
 /* launch on the caller's stream from now on; the handle is used as given (NULL = the legacy
  * default stream).  A fresh context owns a private non-blocking stream. */
@@ -282,10 +291,11 @@ GV_API int gv_grid_finalize_multi(gv_ctx *ctx, int32_t k_decay, const double *co
  * that gv_grid_finalize_multi runs FUSED over peer memory: the raycast sweep sums and clears the
  * binned-beam planes of all ranks itself (no all-reduce), and the finalise kernel sums all
  * ranks' count planes for its slab and writes the finished slab into every rank's grid (no
- * reduce-scatter / all-gather); NCCL is then used only for three one-word barriers.
+ * reduce-scatter / all-gather); the three barriers of that path are flag words in peer memory
+ * (no NCCL call at all).
  * Call gv_ipc_export on every rank after gv_grid_init*, exchange the GV_IPC_BLOB_BYTES blobs
  * (rank order), call gv_ipc_import on every rank.  Re-do after re-initialising the grid. */
-#define GV_IPC_BLOB_BYTES 320
+#define GV_IPC_BLOB_BYTES 448
 GV_API int gv_ipc_export(gv_ctx *ctx, void *blob_out);
 GV_API int gv_ipc_import(gv_ctx *ctx, const void *blobs, int world, int rank);
 /* unmap the peers again: gv_grid_finalize_multi goes back to the NCCL collectives */

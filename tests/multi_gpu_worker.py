@@ -55,6 +55,20 @@ def main():
         assert np.allclose(oc, g.occupancy, rtol=1e-5, atol=0), f"rank {rank}: occupancy"
         hit, miss = ctx.grid_counts()
         assert not hit.any() and not miss.any()
+    # three more batches back to back, nothing read in between: batch k+1 is binned into the second
+    # end-cell plane while batch k's merge (peer barriers, sweep, finalise) is still in flight
+    for rounds in range(3):
+        if f1 > f0:
+            ctx.process_batch(*np.ascontiguousarray(xyz[:, f0 * P:f1 * P]), fo, boxes, bo, gv.accum_params(**prm))
+        ctx.grid_finalize(F, corners, multi=True)
+        for f in range(F):
+            fx = xyz[:, f * P:(f + 1) * P]
+            cam = orc.transform_points(Tc[0], *fx)
+            lab, _, _, _ = orc.project_label(wl.K(), wl.image_w, wl.image_h, *cam, per_frame[f])
+            g.accumulate(Tb, *fx, lab, **prm)
+        g.finalize(F, corners)
+    lo, oc = ctx.grid_download()
+    assert np.array_equal(lo.view(np.uint32), g.log_odds.view(np.uint32)), f"rank {rank}: log_odds after pipelined batches"
     ctx.close()
     dist.barrier()
     if rank == 0:

@@ -276,3 +276,53 @@ def test_fast_path_device_pointers_without_labels(ctx):
     hit, miss = ctx.grid_counts()
     _, g = oracle_batch(wl, xyz, fo, per_frame, Tc, Tb, r_max=wl.r_max)
     assert np.array_equal(hit, g.hit) and np.array_equal(miss, g.miss)
+
+
+@pytest.mark.parametrize("overlap", ["1", "0"])
+def test_pipelined_batches_match_sequential_oracle(overlap):
+    """Five different batches finalised back to back with nothing read in between: batch k+1 is
+    binned into the second end-cell plane while batch k's raycast + finalise still run on the merge
+    stream (GV_OVERLAP=1), or everything on one stream (=0).  The clamp makes the sequence
+    order-sensitive, so the final log-odds equal the oracle's only if every merge saw exactly its
+    own batch."""
+    import torch
+    os.environ["GV_OVERLAP"] = overlap
+    try:
+        c = gv.Context(0)
+    finally:
+        del os.environ["GV_OVERLAP"]
+    try:
+        wl = small(synth.C3, rings=32, azimuth=2048, grid_nx=1024, grid_ny=1024)
+        P = wl.points_per_frame
+        Tc, Tb = synth.camera_extrinsics(1)[0], synth.T_base_lidar()
+        c.set_cameras(wl.K().reshape(1, 9), [[wl.image_w, wl.image_h]], Tc[None])
+        c.grid_init_cells(wl.grid_nx, wl.grid_ny, wl.resolution)
+        c.set_base_transform(Tb)
+        g = oracle_grid(wl)
+        prm = dict(r_max=wl.r_max)
+        batches = []
+        for b in range(5):
+            nf = 3 + b
+            xyz = scan(wl, frames=nf, frame0=10 * b, adversarial=(b % 2 == 1))
+            per = [synth.make_boxes(wl, frame=10 * b + f) for f in range(nf)]
+            fo = (np.arange(nf + 1) * P).astype(np.uint64)
+            bo = np.cumsum([0] + [len(x) for x in per]).astype(np.int32)
+            d = torch.from_numpy(xyz).cuda()
+            d_boxes = torch.from_numpy(np.concatenate(per).view(np.uint8).copy()).cuda()
+            batches.append((xyz, per, fo, bo, d, d_boxes, nf))
+        torch.cuda.synchronize()
+        for xyz, per, fo, bo, d, d_boxes, nf in batches:  # queued without any host wait
+            c.process_batch(d[0], d[1], d[2], fo, d_boxes, bo, gv.accum_params(**prm), None)
+            c.grid_finalize(nf)
+        for xyz, per, fo, bo, d, d_boxes, nf in batches:
+            _, gb = oracle_batch(wl, xyz, fo, per, Tc, Tb, **prm)
+            g.hit += gb.hit
+            g.miss += gb.miss
+            g.finalize(nf)
+        lo, oc = c.grid_download()
+        assert_bits_equal(lo, g.log_odds, "log_odds after 5 pipelined batches")
+        assert rel_close(oc, g.occupancy, OCC_RTOL)
+        st = c.stats()
+        assert st["merges"] == 5 and (st["merge_ms_last"] > 0.0) == (overlap == "1")
+    finally:
+        c.close()
