@@ -349,7 +349,9 @@ def timed_batch(torch, gv, synth, ctx, dev, wl, frames, iters, adversarial=False
     torch.cuda.synchronize()
     st1 = ctx.stats()
     ms_pts = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
-    ms_ray = float(st1["merge_ms_last"])  # on its own stream, overlapped with the next pass's binning
+    ms_ray = float(st1["merge_ms_last"])  # on its own stream when overlapped with the next pass's binning
+    if ms_ray == 0.0:
+        ms_ray = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
     ms = t_a.elapsed_time(t_b) / iters
     per = lambda k: (st1[k] - st0[k]) / iters
     return {"workload": wl.name + (" (adversarial ranges r ~ U(2, sensor_range))" if adversarial else ""),
@@ -572,6 +574,8 @@ def main():
     # raycast + [exchange] + finalise of one step, timed on the stream it runs on (it overlaps the
     # next step's binning, so it is not a summand of ms_per_step)
     ms_final = max_over_ranks(float(st1["merge_ms_last"]))
+    if ms_final == 0.0:  # merge on the caller's stream (one GPU): the events bracket it
+        ms_final = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
 
     # ---- end to end through the host-pointer C ABI (pinned host buffers)
     e2e = None
@@ -646,8 +650,8 @@ def main():
                          "frac": achieved / peak, "traffic": None,
                          "algorithmic_bytes_per_launch": pts_bytes, "ms_per_launch": ms_points},
             "phases_ms": {"fuse_bin": ms_points, "raycast_merge_finalize": ms_final,
-                          "note": "the merge of step k runs on a second stream under the binning of step k+1 "
-                                  "(two end-cell planes); fuse_bin is the kernel's duration in that mix"},
+                          "note": "N > 1: the merge of step k runs on a second stream under the binning of step "
+                                  "k+1 (two end-cell planes), so the two phases are not summands of ms_per_step"},
             "cells_per_s": {"logical": (st1["cells_logical"] - st0["cells_logical"]) / args.steps / (ms_step * 1e-3),
                             "physical": phys / (ms_step * 1e-3),
                             "distinct_ends_per_step": dst / args.steps},

@@ -53,6 +53,7 @@ EXPORTS = [
     "gv_synchronize", "gv_join", "gv_stream", "gv_set_stream", "gv_get_stats",
     "gv_set_cameras", "gv_fuse", "gv_fuse_aos32", "gv_fuse_dev", "gv_transform_points",
     "gv_project_kdtree", "gv_partition_by_label", "gv_segment_ground", "gv_bbox_pose",
+    "gv_box_depths", "gv_pixels_to_3d",
     "gv_grid_init_reference", "gv_grid_init", "gv_grid_get_desc", "gv_grid_reset",
     "gv_grid_upload", "gv_grid_download", "gv_grid_counts_download", "gv_grid_layers_dev",
     "gv_grid_get_index",

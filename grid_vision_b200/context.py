@@ -196,6 +196,24 @@ class Context:
                                            _ptr(labels), C.c_int(nboxes), out), "gv_bbox_pose")
         return list(out)[:nboxes]
 
+    def box_depths(self, uvz, boxes, k=4):
+        """N4: median depth of the k nearest (u, v, depth) triples of every box centre."""
+        uvz = _np(uvz, np.float32).reshape(-1, 3)
+        boxes = _np(boxes, BOX_DTYPE)
+        out = np.empty(max(len(boxes), 1), np.float32)
+        self._check(self._lib.gv_box_depths(self._h, _ptr(uvz), C.c_size_t(len(uvz)), _ptr(boxes),
+                                            C.c_int(len(boxes)), C.c_int(k), _ptr(out)), "gv_box_depths")
+        return out[:len(boxes)].copy()
+
+    def pixels_to_3d(self, boxes, depths, K_inv):
+        boxes = _np(boxes, BOX_DTYPE)
+        depths = _np(depths, np.float32)
+        K_inv = _np(K_inv, np.float64).reshape(9)
+        out = np.empty((max(len(boxes), 1), 3), np.float64)
+        self._check(self._lib.gv_pixels_to_3d(self._h, _ptr(boxes), _ptr(depths), C.c_int(len(boxes)),
+                                              _ptr(K_inv), _ptr(out)), "gv_pixels_to_3d")
+        return out[:len(boxes)].copy()
+
     # ------------------------------------------------------------------ grid
     def grid_init(self, length_x, length_y, resolution, pos_x=0.0, pos_y=0.0):
         self._check(self._lib.gv_grid_init(self._h, C.c_double(length_x), C.c_double(length_y),

@@ -33,7 +33,7 @@ enum {
   S_X, S_Y, S_Z, S_AOS, S_LAB, S_PIX, S_UV, S_BOX_RAW, S_BOX_F4, S_FRAME_OFF, S_BOX_OFF,
   S_TILE_PREFIX, S_TILE_START, S_TILE_END, S_TILE_BOX, S_CELL, S_FLAGS, S_FOOT_IN, S_FOOT_LAB,
   S_RECT, S_SMALL, S_OX, S_OY, S_OZ, S_SCAN0, S_SCAN1, S_SCAN2, S_SCAN3, S_UVZ, S_INDICES,
-  S_LABELS_IN, S_MASKS, S_SET_OFF, S_SWEEP, S_SWEEP_PREFIX, S_BATCH_ENTRY, S_BATCH_MI, S_BATCH_W, S_N2_TAB, S_N2_KEEP, S_N2_OUT, S_N2_OFF, S_N1_PLANES, S_N1_VALID, S_N1_SCORES, S_N1_STATE, S_DEFER, S_FRAMES, S_COUNT
+  S_LABELS_IN, S_MASKS, S_SET_OFF, S_SWEEP, S_SWEEP_PREFIX, S_BATCH_ENTRY, S_BATCH_MI, S_BATCH_W, S_N2_TAB, S_N2_KEEP, S_N2_OUT, S_N2_OFF, S_N1_PLANES, S_N1_VALID, S_N1_SCORES, S_N1_STATE, S_DEFER, S_FRAMES, S_KNN_DEPTH, S_KNN_XYZ, S_COUNT
 };
 
 constexpr size_t kPlanePad = 4096;  // slack cells so multi-GPU slabs can be equal-sized
@@ -70,7 +70,10 @@ struct gv_ctx {
   cudaEvent_t ev_bin_done = nullptr, ev_merge_done[2] = {nullptr, nullptr};
   cudaEvent_t ev_merge_t0 = nullptr, ev_merge_t1 = nullptr;  // timing of the last merge
   bool merge_busy[2] = {false, false}, merge_timed = false;
-  bool overlap = true;  // $GV_OVERLAP=0: finalize runs on the caller's stream
+  int overlap = -1;     // $GV_OVERLAP: 1 finalize on merge_stream, 0 on the caller's stream; default (-1): on
+                        // merge_stream when there are several ranks (there the merge is latency-bound and
+                        // hides under the next batch's binning; on one GPU both are issue-bound and it
+                        // only slows the binning kernel down by what it gains)
   unsigned long long merges = 0;
   unsigned *d_list_count = nullptr;  // work-item counter of the raycast sweep
   SweepEntry *d_sweep = nullptr;     // sweep table for the current start cell
@@ -271,7 +274,7 @@ struct MergeScope {
 int merge_begin(gv_ctx *ctx, MergeScope *sc)
 {
   sc->saved = ctx->stream;
-  sc->active = ctx->overlap && ctx->merge_stream != nullptr;
+  sc->active = (ctx->overlap < 0 ? ctx->world > 1 : ctx->overlap != 0) && ctx->merge_stream != nullptr;
   if (!sc->active) return join_merge(ctx);
   GV_CUDA(cudaEventRecord(ctx->ev_bin_done, ctx->stream));
   GV_CUDA(cudaStreamWaitEvent(ctx->merge_stream, ctx->ev_bin_done, 0));
@@ -905,7 +908,7 @@ int gv_create(gv_ctx **out, int device)
       return GV_ERR_CUDA;
     }
   }
-  if (const char *u = std::getenv("GV_OVERLAP")) ctx->overlap = std::atoi(u) != 0;
+  if (const char *u = std::getenv("GV_OVERLAP")) ctx->overlap = std::atoi(u) != 0 ? 1 : 0;
   ctx->timing = std::getenv("GV_TIMING") != nullptr;
   ctx->use_fast = std::getenv("GV_NO_FAST") == nullptr;
   if (const char *u = std::getenv("GV_FAST_U")) ctx->fast_unroll = std::atoi(u);
@@ -1392,6 +1395,58 @@ int gv_bbox_pose(gv_ctx *ctx, const float *x, const float *y, const float *z, si
   GV_LAUNCH_CHECK();
   GV_CUDA(cudaMemcpyAsync(out, d_out, (size_t)nboxes * sizeof(LShapeDev), cudaMemcpyDeviceToHost,
                           ctx->stream));
+  GV_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GV_OK;
+}
+
+// N4: static-object depth — cloud_detections::computeDepthForBoundingBoxes
+// (ref: src/cloud_detections.cpp:43-87, called at src/grid_vision_node.cpp:179)
+int gv_box_depths(gv_ctx *ctx, const float *uvz, size_t m, const gv_box *boxes, int nboxes, int k,
+                  float *depths_out)
+{
+  if (!ctx) return GV_ERR_INVALID;
+  GV_CUDA(cudaSetDevice(ctx->device));
+  GV_REQUIRE(nboxes >= 0 && k >= 1 && k <= kMaxKnn, GV_ERR_INVALID, "nboxes %d / k %d out of range (k <= %d)",
+             nboxes, k, kMaxKnn);
+  GV_REQUIRE(m < 4294967295ull, GV_ERR_INVALID, "too many image points");
+  if (nboxes == 0) return GV_OK;
+  GV_REQUIRE(boxes && depths_out && (m == 0 || uvz), GV_ERR_INVALID, "boxes / depths_out / uvz is NULL");
+  float *d_uvz, *d_depth;
+  BoxRaw *d_box;
+  GV_TRY(reserve_t(ctx, S_UVZ, 3 * (m ? m : 1), &d_uvz));
+  GV_TRY(reserve_t(ctx, S_BOX_RAW, (size_t)nboxes, &d_box));
+  GV_TRY(reserve_t(ctx, S_KNN_DEPTH, (size_t)nboxes, &d_depth));
+  if (m) GV_CUDA(cudaMemcpyAsync(d_uvz, uvz, 3 * m * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  GV_CUDA(cudaMemcpyAsync(d_box, boxes, (size_t)nboxes * sizeof(BoxRaw), cudaMemcpyHostToDevice, ctx->stream));
+  k_box_knn_depth<<<nboxes, kThreads, 0, ctx->stream>>>(d_uvz, (unsigned)m, d_box, k, d_depth);
+  GV_LAUNCH_CHECK();
+  GV_CUDA(cudaMemcpyAsync(depths_out, d_depth, (size_t)nboxes * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  GV_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GV_OK;
+}
+
+// cloud_detections::pixelTo3D for a list of box centres (ref: src/cloud_detections.cpp:89-103,
+// loop at src/grid_vision_node.cpp:309-335)
+int gv_pixels_to_3d(gv_ctx *ctx, const gv_box *boxes, const float *depths, int nboxes, const double *K_inv,
+                    double *xyz_out)
+{
+  if (!ctx) return GV_ERR_INVALID;
+  GV_CUDA(cudaSetDevice(ctx->device));
+  GV_REQUIRE(nboxes >= 0, GV_ERR_INVALID, "negative box count");
+  if (nboxes == 0) return GV_OK;
+  GV_REQUIRE(boxes && depths && K_inv && xyz_out, GV_ERR_INVALID, "NULL argument");
+  BoxRaw *d_box;
+  float *d_depth;
+  double *d_k;
+  GV_TRY(reserve_t(ctx, S_BOX_RAW, (size_t)nboxes, &d_box));
+  GV_TRY(reserve_t(ctx, S_KNN_DEPTH, (size_t)nboxes, &d_depth));
+  GV_TRY(reserve_t(ctx, S_KNN_XYZ, (size_t)3 * nboxes + 9, &d_k));
+  GV_CUDA(cudaMemcpyAsync(d_box, boxes, (size_t)nboxes * sizeof(BoxRaw), cudaMemcpyHostToDevice, ctx->stream));
+  GV_CUDA(cudaMemcpyAsync(d_depth, depths, (size_t)nboxes * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  GV_CUDA(cudaMemcpyAsync(d_k, K_inv, 9 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  k_pixels_to_3d<<<blocks_for(nboxes, 128), 128, 0, ctx->stream>>>(d_box, d_depth, nboxes, d_k, d_k + 9);
+  GV_LAUNCH_CHECK();
+  GV_CUDA(cudaMemcpyAsync(xyz_out, d_k + 9, (size_t)3 * nboxes * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   GV_CUDA(cudaStreamSynchronize(ctx->stream));
   return GV_OK;
 }

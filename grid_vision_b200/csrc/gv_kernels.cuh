@@ -1718,6 +1718,91 @@ __global__ void k_round_boxes(const BoxRaw *__restrict__ in, int n, float4 *__re
                        __double2float_rd(in[i].x_max), __double2float_rd(in[i].y_max));
 }
 
+// ----------------------------------------------------------------------------------
+// N4: cloud_detections::computeDepthForBoundingBoxes (ref: src/cloud_detections.cpp:43-87;
+// oracle gvo_box_depths).  One CTA per box; the k nearest (u, v, depth) triples of the box centre
+// (cx, cy, 0) are found by k selection rounds over the whole list: round r takes the smallest
+// (distance, index) key greater than round r-1's.  Distance = FLANN's float accumulation
+// ((du*du) + dv*dv) + depth*depth, non-finite triples are not candidates (PCL does not put them in
+// the tree).  Brute force on purpose: at the reference's sizes (1e5 points, <= 50 boxes, k = 4)
+// this is tens of microseconds and has no approximate-search parameter to agree on.
+// ----------------------------------------------------------------------------------
+constexpr int kMaxKnn = 64;
+
+__global__ void __launch_bounds__(kThreads) k_box_knn_depth(const float *__restrict__ uvz, unsigned m,
+                                                            const BoxRaw *__restrict__ boxes, int k,
+                                                            float *__restrict__ depths)
+{
+  __shared__ unsigned long long s_best;
+  __shared__ float s_depth[kMaxKnn];
+  const BoxRaw B = boxes[blockIdx.x];
+  // ref :57-60: centre in double, narrowed to pcl::PointXYZ's floats
+  const float qx = __double2float_rn(__dadd_rn(B.x_min, __ddiv_rn(__dsub_rn(B.x_max, B.x_min), 2.0)));
+  const float qy = __double2float_rn(__dadd_rn(B.y_min, __ddiv_rn(__dsub_rn(B.y_max, B.y_min), 2.0)));
+  unsigned long long last = 0ull;
+  int found = 0;
+  for (int r = 0; r < k; ++r) {
+    if (threadIdx.x == 0) s_best = ~0ull;
+    __syncthreads();
+    unsigned long long best = ~0ull;
+    for (unsigned i = threadIdx.x; i < m; i += kThreads) {
+      const float u = uvz[3 * i], v = uvz[3 * i + 1], z = uvz[3 * i + 2];
+      if (!finite3(u, v, z)) continue;
+      const float du = __fsub_rn(u, qx), dv = __fsub_rn(v, qy);
+      const float d = __fadd_rn(__fadd_rn(__fmul_rn(du, du), __fmul_rn(dv, dv)), __fmul_rn(z, z));
+      // d >= 0: its bit pattern orders like the value, so (bits, index) is the lexicographic key
+      const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | i;
+      if ((r == 0 || key > last) && key < best) best = key;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long t = __shfl_xor_sync(0xffffffffu, best, o);
+      best = t < best ? t : best;
+    }
+    if ((threadIdx.x & 31) == 0 && best != ~0ull) atomicMin(&s_best, best);
+    __syncthreads();
+    const unsigned long long sel = s_best;
+    __syncthreads();
+    if (sel == ~0ull) break;  // fewer than k finite triples
+    last = sel;
+    if (threadIdx.x == 0) s_depth[r] = uvz[3 * (size_t)(unsigned)sel + 2];
+    ++found;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // ref :78-82: std::nth_element at size/2 == element size/2 of the ascending depths
+    for (int j = 1; j < found; ++j) {
+      const float t = s_depth[j];
+      int q = j;
+      while (q > 0 && t < s_depth[q - 1]) {
+        s_depth[q] = s_depth[q - 1];
+        --q;
+      }
+      s_depth[q] = t;
+    }
+    depths[blockIdx.x] = found ? s_depth[found / 2] : -1.0f;  // ref :51 default
+  }
+}
+
+// cloud_detections::pixelTo3D for every box centre (ref: src/cloud_detections.cpp:89-103 called
+// from src/grid_vision_node.cpp:318-325): depth * (K_inv * (cx, cy, 1)), Eigen's left-to-right
+// double accumulation; the centre is a cv::Point2f (floats).
+__global__ void k_pixels_to_3d(const BoxRaw *__restrict__ boxes, const float *__restrict__ depths, int n,
+                               const double *__restrict__ Kinv, double *__restrict__ xyz)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const BoxRaw B = boxes[i];
+  const double px = (double)__double2float_rn(__dadd_rn(B.x_min, __ddiv_rn(__dsub_rn(B.x_max, B.x_min), 2.0)));
+  const double py = (double)__double2float_rn(__dadd_rn(B.y_min, __ddiv_rn(__dsub_rn(B.y_max, B.y_min), 2.0)));
+  const double d = (double)depths[i];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const double t = __dadd_rn(__dadd_rn(__dmul_rn(Kinv[3 * r], px), __dmul_rn(Kinv[3 * r + 1], py)), Kinv[3 * r + 2]);
+    xyz[3 * i + r] = __dmul_rn(d, t);
+  }
+}
+
 // sensor origin -> start cell and continuous index coordinates (single thread)
 struct OriginOut {
   int sx, sy, ok, pad;

@@ -200,6 +200,21 @@ typedef struct {
 GV_API int gv_bbox_pose(gv_ctx *ctx, const float *x, const float *y, const float *z, size_t n,
                         const int16_t *labels, int nboxes, gv_lshape *out);
 
+/* "Next" row N4: depth of the static detections — cloud_detections::computeDepthForBoundingBoxes
+ * (ref: src/cloud_detections.cpp:43-87; decl cloud_detections.hpp:32-35; call site
+ * src/grid_vision_node.cpp:179 with k = k_near, 4 in config/grid_vision_cfg.yaml:20).
+ * uvz: the m (u, v, depth) triples of gv_project_kdtree.  Per box: the k nearest triples of
+ * (centre_x, centre_y, 0) in the tree's 3-D float metric (depth is a coordinate), the median
+ * (element size/2 of the ascending depths), -1 when none.  Exact search; ties in distance go to
+ * the lower index (FLANN leaves them unspecified).  k <= 64. */
+GV_API int gv_box_depths(gv_ctx *ctx, const float *uvz, size_t m, const gv_box *boxes, int nboxes,
+                         int k, float *depths_out);
+/* cloud_detections::pixelTo3D (ref: src/cloud_detections.cpp:89-103) for every box centre, as
+ * GridVision::convertPixelsTo3D loops it (ref: src/grid_vision_node.cpp:309-335) before the TF
+ * hop: xyz_out[3i..] = depths[i] * (K_inv * (centre_x, centre_y, 1)), camera frame, doubles. */
+GV_API int gv_pixels_to_3d(gv_ctx *ctx, const gv_box *boxes, const float *depths, int nboxes,
+                           const double *K_inv, double *xyz_out);
+
 /* --------------------------------------------------------- grid state (R6) --- */
 /* ref: OccupancyGridMap::OccupancyGridMap, src/occupancy_grid.cpp:4-14
  * (decl include/grid_vision/occupancy_grid.hpp:16): size = round(length/res), centre

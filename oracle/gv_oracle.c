@@ -172,6 +172,68 @@ size_t gvo_project_kdtree(const double K[9], const float *x, const float *y, con
   return m;
 }
 
+/* N4: cloud_detections::computeDepthForBoundingBoxes (src/cloud_detections.cpp:43-87) on the
+ * (u, v, depth) triples buildKDTree emitted.  The tree is 3-D: depth is its third coordinate
+ * (:28-30) and the query's is 0 (:60), so "nearest" minimises (u-cx)^2 + (v-cy)^2 + depth^2 in
+ * FLANN's float accumulation order (pcl::KdTreeFLANN's default flann::L2_Simple<float>: one
+ * `result += diff*diff` per coordinate).  Non-finite points are not in the tree (PCL drops them
+ * when it converts the cloud).  Median = element size/2 of the ascending depths (:78-82);
+ * -1 when nothing was found (:51).  FLANN's order among equal distances is unspecified: lower
+ * index first here. */
+void gvo_box_depths(const float *uvz, size_t m, const void *boxes40, int nb, int k, float *depths)
+{
+  const gvo_box *B = (const gvo_box *)boxes40;
+  if (k > 64) k = 64;
+  for (int b = 0; b < nb; ++b) {
+    depths[b] = -1.0f;
+    /* :57-60 centre in double (x_min + (x_max - x_min) / 2.0f), narrowed to the float fields */
+    const float qx = (float)(B[b].x_min + ((B[b].x_max - B[b].x_min) / 2.0f));
+    const float qy = (float)(B[b].y_min + ((B[b].y_max - B[b].y_min) / 2.0f));
+    float bd[64];
+    size_t bi[64];
+    int found = 0;
+    for (size_t i = 0; i < m; ++i) {
+      const float u = uvz[3 * i], v = uvz[3 * i + 1], z = uvz[3 * i + 2];
+      if (!(isfinite(u) && isfinite(v) && isfinite(z))) continue;
+      float d = 0.0f, diff;
+      diff = u - qx; d += diff * diff;
+      diff = v - qy; d += diff * diff;
+      diff = z - 0.0f; d += diff * diff;
+      if (found == k && !(d < bd[k - 1])) continue; /* ties keep the earlier index */
+      int pos = found < k ? found : k - 1;
+      while (pos > 0 && d < bd[pos - 1]) {
+        bd[pos] = bd[pos - 1];
+        bi[pos] = bi[pos - 1];
+        --pos;
+      }
+      bd[pos] = d;
+      bi[pos] = i;
+      if (found < k) ++found;
+    }
+    if (found == 0 || k <= 0) continue;
+    float dv[64];
+    for (int j = 0; j < found; ++j) dv[j] = uvz[3 * bi[j] + 2];
+    for (int j = 1; j < found; ++j) { /* ascending */
+      const float t = dv[j];
+      int q = j;
+      while (q > 0 && t < dv[q - 1]) { dv[q] = dv[q - 1]; --q; }
+      dv[q] = t;
+    }
+    depths[b] = dv[found / 2];
+  }
+}
+
+/* cloud_detections::pixelTo3D (src/cloud_detections.cpp:89-103): depth * (K_inv * (u, v, 1)),
+ * Eigen's 3x3 * 3x1 accumulated left to right in double. */
+void gvo_pixel_to_3d(const double Kinv[9], float px, float py, float depth, double out[3])
+{
+  const double h[3] = {(double)px, (double)py, 1.0};
+  for (int r = 0; r < 3; ++r) {
+    const double t = (Kinv[3 * r] * h[0] + Kinv[3 * r + 1] * h[1]) + Kinv[3 * r + 2] * h[2];
+    out[r] = (double)depth * t;
+  }
+}
+
 /* ------------------------------------------------------------------------- */
 /* R6  grid geometry (grid_map_core GridMap::setGeometry / setPosition)      */
 /* ------------------------------------------------------------------------- */

@@ -205,6 +205,9 @@ typedef struct {
 
 int32_t gvo_radius_outlier_keep(const float *x, const float *y, const float *z, size_t n,
                                 double radius, int32_t min_neighbors, uint8_t *keep);
+/* N4 (src/cloud_detections.cpp:43-103) */
+void gvo_box_depths(const float *uvz, size_t m, const void *boxes40, int nb, int k, float *depths);
+void gvo_pixel_to_3d(const double Kinv[9], float px, float py, float depth, double out[3]);
 void gvo_bbox_pose(const float *x, const float *y, const float *z, size_t n, gvo_lshape *out);
 
 /* N3 (next row): grid_map_ros toOccupancyGrid(layer "occupancy", 0, 1) cell conversion

@@ -166,6 +166,23 @@ def project_kdtree(K, x, y, z):
     return uvz[:m].copy()
 
 
+def box_depths(uvz, boxes, k=4):
+    """N4: cloud_detections::computeDepthForBoundingBoxes on (u, v, depth) triples."""
+    uvz = np.ascontiguousarray(uvz, dtype=np.float32).reshape(-1, 3)
+    boxes = np.ascontiguousarray(boxes, dtype=BOX_DTYPE)
+    out = np.empty(max(len(boxes), 1), np.float32)
+    lib().gvo_box_depths(_p(uvz, C.c_float), C.c_size_t(len(uvz)), C.c_void_p(boxes.ctypes.data),
+                         C.c_int(len(boxes)), C.c_int(k), _p(out, C.c_float))
+    return out[:len(boxes)].copy()
+
+
+def pixel_to_3d(K_inv, px, py, depth):
+    Ki = np.ascontiguousarray(K_inv, dtype=np.float64).reshape(9)
+    out = np.empty(3, np.float64)
+    lib().gvo_pixel_to_3d(_p(Ki, C.c_double), C.c_float(px), C.c_float(py), C.c_float(depth), _p(out, C.c_double))
+    return out
+
+
 def bresenham_cells(sx, sy, ex, ey):
     n = max(abs(ex - sx), abs(ey - sy)) + 1
     out = np.empty((n, 2), np.int32)
