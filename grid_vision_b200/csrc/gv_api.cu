@@ -129,9 +129,9 @@ struct gv_ctx {
   int *d_barrier = nullptr;
   // optional stage timing of gv_grid_finalize_multi ($GV_TIMING=1): events + accumulated ms
   bool timing = false;
-  cudaEvent_t tev[8] = {};
+  cudaEvent_t tev[12] = {};
   int tev_n = 0;
-  double t_acc[8] = {};
+  double t_acc[12] = {};
   long t_cnt = 0;
 
   int fail(int code, const char *fmt, ...)

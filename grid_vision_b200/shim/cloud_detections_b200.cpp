@@ -1,8 +1,8 @@
-// cloud_detections_b200.cpp — drop-in definitions of the three hot-path functions of namespace
+// cloud_detections_b200.cpp — drop-in definitions of the four hot-path functions of namespace
 // cloud_detections, with the reference's exact signatures
 // (ref: include/grid_vision/cloud_detections.hpp:29-30,46-48,50-52), over the C ABI.
 //
-// Build it INSTEAD of the bodies at ref: src/cloud_detections.cpp:8-40, 250-298, 300-321 (guard
+// Build it INSTEAD of the bodies at ref: src/cloud_detections.cpp:8-40, 43-87, 250-298, 300-321 (guard
 // those with `#ifndef GRID_VISION_B200`); the rest of that file
 // (segmentGroundPlane, bboxPoseEstimation, computePCABoundingBox, ...) keeps running unchanged.
 #include "grid_vision/cloud_detections.hpp"
@@ -66,6 +66,32 @@ namespace cloud_detections
     {
       kdtree.setInputCloud(image_points);
     }
+  }
+
+  // ref: src/cloud_detections.cpp:43-87 — the k-NN median depth of every box on the GPU (exact
+  // brute-force search over the (u, v, depth) triples; the FLANN tree argument is not consulted).
+  std::vector<float>
+  computeDepthForBoundingBoxes(pcl::KdTreeFLANN<pcl::PointXYZ> &,
+                               pcl::PointCloud<pcl::PointXYZ>::Ptr image_points,
+                               const std::vector<BoundingBox> &bboxes, uint16_t k)
+  {
+    std::vector<float> depths(bboxes.size(), -1.0f);
+    gv_ctx *ctx = gv_shim::context();
+    const size_t m = image_points ? image_points->points.size() : 0;
+    if(!ctx || bboxes.empty() || m == 0 || k == 0)
+      return depths;
+    std::vector<float> uvz(3 * m);
+    for(size_t i = 0; i < m; ++i)
+    {
+      uvz[3 * i + 0] = image_points->points[i].x;
+      uvz[3 * i + 1] = image_points->points[i].y;
+      uvz[3 * i + 2] = image_points->points[i].z;
+    }
+    gv_shim::ok(ctx,
+                gv_box_depths(ctx, uvz.data(), m, reinterpret_cast<const gv_box *>(bboxes.data()),
+                              static_cast<int>(bboxes.size()), k > 64 ? 64 : k, depths.data()),
+                "gv_box_depths");
+    return depths;
   }
 
   // ref: src/cloud_detections.cpp:250-298

@@ -73,6 +73,36 @@ size_t ref_build_kdtree(const float *x, const float *y, const float *z, size_t n
   return img->points.size();
 }
 
+// cloud_detections::computeDepthForBoundingBoxes (src/cloud_detections.cpp:43-87) on (u, v, depth)
+// triples as buildKDTree leaves them (tree over the same cloud), k as the node passes k_near_
+void ref_box_depths(const float *uvz, size_t m, const BoundingBox *boxes, int nb, int k, float *depths)
+{
+  pcl::PointCloud<pcl::PointXYZ>::Ptr img(new pcl::PointCloud<pcl::PointXYZ>);
+  img->points.resize(m);
+  for (size_t i = 0; i < m; ++i) {
+    img->points[i].x = uvz[3 * i + 0];
+    img->points[i].y = uvz[3 * i + 1];
+    img->points[i].z = uvz[3 * i + 2];
+  }
+  pcl::KdTreeFLANN<pcl::PointXYZ> tree;
+  if (!img->empty()) tree.setInputCloud(img);
+  std::vector<BoundingBox> bb(boxes, boxes + nb);
+  const std::vector<float> d = cloud_detections::computeDepthForBoundingBoxes(tree, img, bb, (uint16_t)k);
+  for (int i = 0; i < nb; ++i) depths[i] = d[i];
+}
+
+// cloud_detections::pixelTo3D (src/cloud_detections.cpp:89-103)
+void ref_pixel_to_3d(const double *Kinv, float px, float py, float depth, double *out)
+{
+  Eigen::Matrix3d Ki;
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) Ki(r, c) = Kinv[3 * r + c];
+  const geometry_msgs::msg::Point p = cloud_detections::pixelTo3D(cv::Point2f(px, py), depth, Ki);
+  out[0] = p.x;
+  out[1] = p.y;
+  out[2] = p.z;
+}
+
 // cloud_detections::computeBBoxPose error convention (src/cloud_detections.cpp:308-309):
 // an empty ground-removed cloud yields an empty result
 int ref_compute_bbox_pose_empty()

@@ -353,11 +353,36 @@ inline unsigned compute3DCentroid(const PointCloud<P> &c, Eigen::Vector4f &o)
   o[2] /= n;
   return (unsigned)c.points.size();
 }
+// pcl::KdTreeFLANN stand-in: an EXACT k-nearest-neighbour search (what FLANN's single KD-tree
+// returns with PCL's default exact parameters), brute force.  Distance = flann::L2_Simple<float>
+// (one `result += diff*diff` per coordinate, float); non-finite points are not indexed (PCL's
+// convertCloudToArray drops them); k is clamped to the number of indexed points; results are
+// ascending in distance, ties by lower index (upstream leaves ties unspecified).
 template <typename P>
-struct KdTreeFLANN {  // inert: FLANN is not on the hot path, only the projection loop is
+struct KdTreeFLANN {
   typename PointCloud<P>::Ptr in;
   void setInputCloud(const typename PointCloud<P>::Ptr &c) { in = c; }
-  int nearestKSearch(const P &, int, std::vector<int> &, std::vector<float> &) { return 0; }
+  int nearestKSearch(const P &q, int k, std::vector<int> &idx, std::vector<float> &dist)
+  {
+    idx.clear();
+    dist.clear();
+    if (!in || k <= 0) return 0;
+    for (size_t i = 0; i < in->points.size(); ++i) {
+      const P &p = in->points[i];
+      if (!(std::isfinite(p.x) && std::isfinite(p.y) && std::isfinite(p.z))) continue;
+      float d = 0.0f, diff;
+      diff = p.x - q.x; d += diff * diff;
+      diff = p.y - q.y; d += diff * diff;
+      diff = p.z - q.z; d += diff * diff;
+      if ((int)idx.size() == k && !(d < dist.back())) continue;
+      size_t pos = idx.size();
+      if ((int)idx.size() < k) { idx.push_back(0); dist.push_back(0.0f); } else pos = (size_t)k - 1;
+      while (pos > 0 && d < dist[pos - 1]) { dist[pos] = dist[pos - 1]; idx[pos] = idx[pos - 1]; --pos; }
+      dist[pos] = d;
+      idx[pos] = (int)i;
+    }
+    return (int)idx.size();
+  }
 };
 }  // namespace pcl
 

@@ -222,3 +222,49 @@ def test_finalize_restates_reference_updates(ref):
         ref.ref_update_map_poses(rg.h, p(poses), C.c_int(n))
         og.finalize(1, orc.pose_corners(poses))
         same_grid(rg, og)
+
+
+# ------------------------------------------------------------------------- N4: k-NN median depth, pixelTo3D
+def depth_case(rng, m, nb, W=416, H=416):
+    uvz = np.stack([rng.uniform(-50, W + 50, m), rng.uniform(-50, H + 50, m), rng.uniform(0.2, 80.0, m)], 1).astype(f32)
+    uvz[rng.integers(0, m, max(1, m // 50)), 2] = np.nan      # NaN depths pass buildKDTree's z <= 0 test
+    uvz[rng.integers(0, m, max(1, m // 80)), 0] = np.inf
+    boxes = random_boxes(rng, nb, W, H, integer=False)
+    return np.ascontiguousarray(uvz), boxes
+
+
+@pytest.mark.parametrize("k", [1, 4, 10])
+def test_box_depths_oracle_vs_reference(ref, k):
+    """The reference's own computeDepthForBoundingBoxes (over the exact-search FLANN stand-in) and the
+    oracle restatement: box centre in float, 3-D float metric with depth as a coordinate, median."""
+    rng = np.random.default_rng(40 + k)
+    for m, nb in ((5000, 37), (3, 5), (0, 4), (1, 2)):
+        uvz, boxes = depth_case(rng, m, nb) if m else (np.zeros((0, 3), f32), random_boxes(rng, nb, 416, 416))
+        got = np.empty(nb, f32)
+        ref.ref_box_depths(p(uvz), C.c_size_t(len(uvz)), p(boxes), C.c_int(nb), C.c_int(k), p(got))
+        exp = orc.box_depths(uvz, boxes, k)
+        assert np.array_equal(got.view(np.uint32), exp.view(np.uint32)), (m, nb, k)
+        if m == 0:
+            assert np.all(exp == -1.0)
+
+
+def test_box_depths_depth_is_a_coordinate(ref):
+    """A far point right at the box centre loses to a near point a few pixels away: the tree is built
+    over (u, v, depth), src/cloud_detections.cpp:28-30, and the query's third coordinate is 0 (:60)."""
+    boxes = orc.make_boxes([[100, 100, 200, 200]])
+    uvz = np.array([[150, 150, 30.0], [153, 150, 2.0], [150, 156, 2.5]], f32)
+    exp = orc.box_depths(uvz, boxes, 1)
+    got = np.empty(1, f32)
+    ref.ref_box_depths(p(uvz), C.c_size_t(3), p(boxes), C.c_int(1), C.c_int(1), p(got))
+    assert exp[0] == got[0] == f32(2.0)
+    assert orc.box_depths(uvz, boxes, 3)[0] == f32(2.5)  # median of {2, 2.5, 30}: element 3 // 2 ascending
+
+
+def test_pixel_to_3d_oracle_vs_reference(ref):
+    rng = np.random.default_rng(9)
+    Ki = np.ascontiguousarray(np.linalg.inv(K416))
+    for _ in range(200):
+        px, py, d = f32(rng.uniform(0, 416)), f32(rng.uniform(0, 416)), f32(rng.uniform(0.1, 90))
+        got = np.empty(3, np.float64)
+        ref.ref_pixel_to_3d(p(Ki), C.c_float(px), C.c_float(py), C.c_float(d), p(got))
+        assert np.array_equal(got.view(np.uint64), orc.pixel_to_3d(Ki, px, py, d).view(np.uint64))
