@@ -7,6 +7,7 @@
 #include "gv_kernels.cuh"
 #include "gv_points_fast.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>

@@ -7,6 +7,13 @@
 #include <cstring>
 #include <optional>
 
+#ifdef GV_SHIM_BUILD
+#include "transform_lidar_to_camera_b200.hpp"
+#define GV_TRANSFORM_CLOUD gv_shim::transformPointCloud
+#else
+#define GV_TRANSFORM_CLOUD pcl_ros::transformPointCloud
+#endif
+
 static_assert(sizeof(BoundingBox) == 40, "BoundingBox layout (object_detection.hpp:27-32)");
 
 extern "C" {
@@ -71,6 +78,34 @@ size_t ref_build_kdtree(const float *x, const float *y, const float *z, size_t n
     uvz[3 * i + 2] = img->points[i].z;
   }
   return img->points.size();
+}
+
+// The compute call of GridVision::transformLidarToCamera (src/grid_vision_node.cpp:296-304):
+// tf2::Transform -> pcl_ros::transformPointCloud.  R: row-major 3x3 doubles, t: origin.
+void ref_transform_cloud(const float *x, const float *y, const float *z, size_t n, int is_dense, const double *R,
+                         const double *t, float *ox, float *oy, float *oz, float *intensity_out)
+{
+  pcl::PointCloud<pcl::PointXYZI> in, out;
+  in.points.resize(n);
+  in.is_dense = is_dense != 0;
+  for (size_t i = 0; i < n; ++i) {
+    in.points[i].x = x[i];
+    in.points[i].y = y[i];
+    in.points[i].z = z[i];
+    in.points[i].intensity = (float)i;
+  }
+  tf2::Transform tf;
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) tf.basis[r].v[c] = R[3 * r + c];
+    tf.origin.v[r] = t[r];
+  }
+  GV_TRANSFORM_CLOUD(in, out, tf);
+  for (size_t i = 0; i < n; ++i) {
+    ox[i] = out.points[i].x;
+    oy[i] = out.points[i].y;
+    oz[i] = out.points[i].z;
+    intensity_out[i] = out.points[i].intensity;
+  }
 }
 
 // cloud_detections::computeDepthForBoundingBoxes (src/cloud_detections.cpp:43-87) on (u, v, depth)

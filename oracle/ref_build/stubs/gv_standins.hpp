@@ -219,6 +219,25 @@ struct Quaternion {
   double z() const { return q[2]; }
   double w() const { return q[3]; }
 };
+// tf2::Transform as pcl_ros consumes it: a 3x3 double basis (rows addressable, elements by
+// x()/y()/z()) and a double origin
+struct Vector3 {
+  double v[3] = {0, 0, 0};
+  double x() const { return v[0]; }
+  double y() const { return v[1]; }
+  double z() const { return v[2]; }
+};
+struct Matrix3x3 {
+  Vector3 r[3];
+  const Vector3 &operator[](int i) const { return r[i]; }
+  Vector3 &operator[](int i) { return r[i]; }
+};
+struct Transform {
+  Matrix3x3 basis;
+  Vector3 origin;
+  const Matrix3x3 &getBasis() const { return basis; }
+  const Vector3 &getOrigin() const { return origin; }
+};
 }  // namespace tf2
 
 // ------------------------------------------------------------------------------ OpenCV
@@ -385,6 +404,36 @@ struct KdTreeFLANN {
   }
 };
 }  // namespace pcl
+
+// pcl_ros::transformPointCloud(in, out, tf2::Transform) as the node calls it
+// (src/grid_vision_node.cpp:304).  RECALLED FROM UPSTREAM (pcl_ros transforms.hpp + pcl
+// common/impl/transforms.hpp), unverified offline: the tf2 transform becomes an Eigen::Matrix4f
+// (doubles narrowed to float), the cloud is copied (every field), and each point's xyz becomes
+// Transformer<float>::se3: c0*x + (c1*y + (c2*z + c3)) per row; with is_dense == false a point
+// with a non-finite coordinate is left as it is.
+namespace pcl_ros {
+template <typename P>
+inline void transformPointCloud(const pcl::PointCloud<P> &in, pcl::PointCloud<P> &out, const tf2::Transform &t)
+{
+  float m[3][4];
+  for (int r = 0; r < 3; ++r) {
+    m[r][0] = (float)t.getBasis()[r].x();
+    m[r][1] = (float)t.getBasis()[r].y();
+    m[r][2] = (float)t.getBasis()[r].z();
+  }
+  m[0][3] = (float)t.getOrigin().x();
+  m[1][3] = (float)t.getOrigin().y();
+  m[2][3] = (float)t.getOrigin().z();
+  out = in;
+  for (auto &p : out.points) {
+    if (!in.is_dense && !(std::isfinite(p.x) && std::isfinite(p.y) && std::isfinite(p.z))) continue;
+    const float x = p.x, y = p.y, z = p.z;
+    p.x = m[0][0] * x + (m[0][1] * y + (m[0][2] * z + m[0][3]));
+    p.y = m[1][0] * x + (m[1][1] * y + (m[1][2] * z + m[1][3]));
+    p.z = m[2][0] * x + (m[2][1] * y + (m[2][2] * z + m[2][3]));
+  }
+}
+}  // namespace pcl_ros
 
 // ------------------------------------------------------------------------------ grid_map
 // grid_map_core GridMap, restated (RECALLED FROM UPSTREAM, unverified offline) for a map that

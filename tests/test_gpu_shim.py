@@ -109,3 +109,21 @@ def test_occupancy_grid_map_drop_in(libs, like_node):
         lb, ob = b.read()
         assert np.array_equal(la.view(np.uint32), lb.view(np.uint32)), f"log_odds, step {k}"
         assert np.all(np.abs(oa - ob) <= 1e-5 * np.maximum(np.abs(oa), np.abs(ob))), f"occupancy, step {k}"
+
+
+@pytest.mark.parametrize("is_dense", [False, True])
+def test_transform_lidar_to_camera_drop_in(libs, is_dense):
+    """gv_shim::transformPointCloud (the replacement for the pcl_ros call inside
+    GridVision::transformLidarToCamera, src/grid_vision_node.cpp:304) vs the stand-in pcl_ros path."""
+    from tests.test_oracle_vs_ref import rigid, transform_cloud
+    ref, shim = libs
+    rng = np.random.default_rng(6)
+    xyz = random_cloud(rng, 200000)
+    R, t = rigid(3)
+    exp = transform_cloud(ref, xyz, R, t, is_dense)
+    got = transform_cloud(shim, xyz, R, t, is_dense)
+    for a, b in zip(got, exp):
+        ab, bb = a.view(np.uint32).copy(), b.view(np.uint32).copy()
+        nan = np.isnan(a) & np.isnan(b)
+        ab[nan] = bb[nan] = 0
+        assert np.array_equal(ab, bb)

@@ -268,3 +268,47 @@ def test_pixel_to_3d_oracle_vs_reference(ref):
         got = np.empty(3, np.float64)
         ref.ref_pixel_to_3d(p(Ki), C.c_float(px), C.c_float(py), C.c_float(d), p(got))
         assert np.array_equal(got.view(np.uint64), orc.pixel_to_3d(Ki, px, py, d).view(np.uint64))
+
+
+# ------------------------------------------------------------------------- R1 through the node's call
+def transform_cloud(lib, xyz, R, t, is_dense):
+    x, y, z = (np.ascontiguousarray(a, f32) for a in xyz)
+    n = x.size
+    ox, oy, oz, it = (np.empty(n, f32) for _ in range(4))
+    R = np.ascontiguousarray(R, np.float64)
+    t = np.ascontiguousarray(t, np.float64)
+    lib.ref_transform_cloud(p(x), p(y), p(z), C.c_size_t(n), C.c_int(int(is_dense)), p(R), p(t), p(ox), p(oy), p(oz),
+                            p(it))
+    assert np.array_equal(it, np.arange(n, dtype=f32))  # the other fields of every point are copied
+    return ox, oy, oz
+
+
+def rigid(seed):
+    rng = np.random.default_rng(seed)
+    q = rng.normal(size=4)
+    q /= np.linalg.norm(q)
+    w, x, y, z = q
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                  [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                  [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    return R, rng.uniform(-3, 3, 3)
+
+
+@pytest.mark.parametrize("is_dense", [False, True])
+def test_transform_lidar_to_camera_oracle_vs_pcl_ros_standin(ref, is_dense):
+    """GridVision::transformLidarToCamera's compute call (src/grid_vision_node.cpp:296-304) through the
+    pcl_ros stand-in vs the oracle's R1 (gvo_transform_points) on the narrowed float matrix."""
+    rng = np.random.default_rng(5)
+    xyz = random_cloud(rng, 50000)
+    for seed in (1, 2):
+        R, t = rigid(seed)
+        got = transform_cloud(ref, xyz, R, t, is_dense)
+        T = np.eye(4, dtype=f32)
+        T[:3, :3] = R.astype(f32)
+        T[:3, 3] = t.astype(f32)
+        exp = orc.transform_points(T, *xyz, is_dense=is_dense)
+        for a, b in zip(got, exp):
+            ab, bb = a.view(np.uint32).copy(), b.view(np.uint32).copy()
+            nan = np.isnan(a) & np.isnan(b)
+            ab[nan] = bb[nan] = 0
+            assert np.array_equal(ab, bb)
