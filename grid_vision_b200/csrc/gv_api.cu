@@ -6,6 +6,7 @@
 #include "gridvision_b200.h"
 #include "gv_kernels.cuh"
 #include "gv_points_fast.cuh"
+#include "gv_points_pair.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -86,7 +87,8 @@ struct gv_ctx {
   bool use_fast = true;  // $GV_NO_FAST=1 forces the generic k_points (A/B measurements)
   int fast_unroll = 2;   // $GV_FAST_U: points per thread per iteration of k_points_fast
   bool col_hoist = false; // $GV_COL_HOIST=1: k_points_col keeps FastHot in registers (fewer instructions, 3 CTAs/SM)
-  int fast_kind = 0;     // $GV_FAST_KIND: 0 k_points_col (default), 1 k_points_tma, 2 k_points_fast
+  int fast_kind = 0;     // $GV_FAST_KIND: 0 k_points_pair where the layout allows it, else k_points_col (default),
+                         // 1 k_points_tma, 2 k_points_fast, 3 k_points_col always
   bool tma_hoist = false; // $GV_TMA_HOIST=1: k_points_tma keeps FastHot in registers instead of the constant bank
   bool use_tma = true;   // $GV_NO_TMA=1: k_points_fast (per-tile CTAs, LDG) instead of k_points_tma
   int fast_agg = -1;     // $GV_FAST_AGG: 0 one RED per beam, 1 match-any groups, 2 adjacent runs;
@@ -112,6 +114,7 @@ struct gv_ctx {
   std::vector<int4> c_tbox;
   std::vector<uint4> c_frames;   // per-frame records for k_points_col
   unsigned c_max_pts = 0;        // largest frame (points)
+  bool c_pair_ok = false;        // every frame offset and size even (k_points_pair)
   int c_tile_pts = 0, c_max_boxes = 0;
   bool c_on_device = false, c_valid = false;
 
@@ -1883,16 +1886,44 @@ static int launch_points_fast(gv_ctx *ctx, FastArgs &f, bool bounded, bool tma, 
   return GV_OK;
 }
 
-// k_points_col over frames [frame0, frame0 + nframes): grid = (column blocks, frame groups)
+// Thresholds of k_points_pair's certified image test and the constants of its tile lookup, from
+// E(q) = e6 |q| + e0 (fill_fast_args).  Everything is worked out in double and rounded to the
+// safe side: a threshold that is too strict only defers a few more points.
+static void fill_pair_args(const FastArgs &f, PairArgs &p)
+{
+  memset(&p, 0, sizeof(p));
+  p.one = 1.0f;
+  const FastWarm &w = f.warm;
+  const double e6 = w.e6, slack = 1.0 + 4.76837158203125e-07;  // 1 + 2^-21
+  struct Axis { double W, e0; float *half, *ain, *aout, *e; };
+  Axis ax[2] = {{(double)w.Wf, (double)w.e0u, &p.half_w, &p.ain_u, &p.aout_u, &p.eu},
+                {(double)w.Hf, (double)w.e0v, &p.half_h, &p.ain_v, &p.aout_v, &p.ev}};
+  for (const Axis &a : ax) {
+    const double half = 0.5 * a.W;                      // exact in binary32 (W is an image size)
+    const double e = (e6 * (a.W + 1.0) + a.e0) * 1.001;  // >= E(q) for every |q| <= W + 1
+    *a.half = (float)half;
+    *a.e = std::nextafterf((float)e, INFINITY);
+    // |RN(q - W/2)| < ain  =>  E < q < W - E, hence every value within E(q) of q is in [0, W)
+    *a.ain = std::nextafterf((float)(half - (double)*a.e - a.W * 4.76837158203125e-07), 0.0f);
+    // |RN(q - W/2)| > aout  =>  q - E(q) >= W or q + E(q) < 0
+    *a.aout = std::nextafterf((float)(((a.W + a.e0) / (1.0 - e6) - half) * slack), INFINITY);
+  }
+  p.inv_tile = 1.0f / (float)(1 << f.mask_shift);
+  p.mask_bias = 0x4340u * (unsigned)(f.mask_tx + 1);
+}
+
+// k_points_col / k_points_pair over frames [frame0, frame0 + nframes): grid = (column blocks, frame groups)
 static int launch_points_col(gv_ctx *ctx, FastArgs &f, bool bounded, int frame0, int nframes, unsigned max_pts)
 {
   if (nframes <= 0 || max_pts == 0) return GV_OK;
   f.frame0 = frame0;
   f.nframes = nframes;
-  const unsigned cols = (max_pts + kThreads - 1) / kThreads;
+  // k_points_pair: one thread per pair of adjacent points
+  const unsigned per_thread = f.pair ? 2u : 1u;
+  const unsigned cols = ((max_pts + per_thread - 1) / per_thread + kThreads - 1) / kThreads;
   // enough CTAs for ~16 waves of 5 CTAs per SM, as few frame groups as that allows: the longer a
   // thread stays on its beam index, the more of the beam's repeats it merges before the RED
-  const unsigned want = (unsigned)ctx->num_sms * 5u * 16u;
+  const unsigned want = (unsigned)ctx->num_sms * (f.pair ? (unsigned)GV_PAIR_MINB * 12u : 5u * 16u);
   unsigned groups = (want + cols - 1) / cols;
   if (groups > (unsigned)nframes) groups = (unsigned)nframes;
   if (groups < 1u) groups = 1u;
@@ -1919,7 +1950,20 @@ static int launch_points_col(gv_ctx *ctx, FastArgs &f, bool bounded, int frame0,
     else if (lab) GV_COL_LAUNCH(false, true, ZZ);      \
     else GV_COL_LAUNCH(false, false, ZZ);              \
   } while (0)
-  if (zg) GV_COL_BL(true);
+  if (f.pair) {
+    PairArgs pa;
+    fill_pair_args(f, pa);
+#define GV_PAIR_BL(ZZ)                                                                                \
+  do {                                                                                                \
+    if (bounded && lab) k_points_pair<true, true, ZZ><<<grid, kThreads, 0, ctx->stream>>>(f, pa);      \
+    else if (bounded) k_points_pair<true, false, ZZ><<<grid, kThreads, 0, ctx->stream>>>(f, pa);       \
+    else if (lab) k_points_pair<false, true, ZZ><<<grid, kThreads, 0, ctx->stream>>>(f, pa);           \
+    else k_points_pair<false, false, ZZ><<<grid, kThreads, 0, ctx->stream>>>(f, pa);                   \
+  } while (0)
+    if (zg) GV_PAIR_BL(true);
+    else GV_PAIR_BL(false);
+#undef GV_PAIR_BL
+  } else if (zg) GV_COL_BL(true);
   else GV_COL_BL(false);
 #undef GV_COL_BL
 #undef GV_COL_LAUNCH
@@ -1994,8 +2038,10 @@ static int process_batch_impl(gv_ctx *ctx, const float *px, const float *py, con
     const std::vector<unsigned long long> &fo = ctx->c_foff;
     ctx->c_frames.resize((size_t)nframes);
     ctx->c_max_pts = 0;
+    ctx->c_pair_ok = true;
     for (int f = 0; f < nframes; ++f) {
       const unsigned long long np = fo[f + 1] - fo[f];
+      if ((fo[f] | np) & 1ull) ctx->c_pair_ok = false;
       GV_REQUIRE(np < 4294967295ull, GV_ERR_INVALID, "frame %d too large", f);
       if (np > ctx->c_max_pts) ctx->c_max_pts = (unsigned)np;
       ctx->c_frames[f] = make_uint4((unsigned)(fo[f] & 0xffffffffull), (unsigned)(fo[f] >> 32), (unsigned)np,
@@ -2124,7 +2170,7 @@ static int process_batch_impl(gv_ctx *ctx, const float *px, const float *py, con
   if (fast) {
     // ballot-word bitmap of deferred points: all-zero between launches (k_points_deferred clears
     // what k_points_fast set), so it is zeroed only when the slot is (re)allocated
-    const bool col = ctx->fast_kind == 0;
+    const bool col = ctx->fast_kind == 0 || ctx->fast_kind == 3;
     const unsigned defer_stride = (ctx->c_max_pts + 31u) / 32u;
     const size_t nwords = col ? (size_t)nframes * defer_stride : (size_t)ntiles * (size_t)(tile_pts >> 5);
     unsigned *d_defer = nullptr;
@@ -2137,6 +2183,9 @@ static int process_batch_impl(gv_ctx *ctx, const float *px, const float *py, con
     fa.frames = d_frames;
     fa.defer_stride = defer_stride;
     fa.col_mode = col ? 1 : 0;
+    // k_points_pair: 64-bit point loads and 32-bit label stores at even point indices
+    fa.pair = col && ctx->fast_kind == 0 && ctx->c_pair_ok &&
+              ((((uintptr_t)d_x | (uintptr_t)d_y | (uintptr_t)d_z) & 7u) == 0) && (((uintptr_t)d_lab & 3u) == 0);
     // bulk copies need 16-byte aligned sources and sizes: plane pointers aligned, every frame
     // boundary (hence every tile start and size) a multiple of 4 points
     tma = ctx->use_tma && a.vec_ok && tile_pts <= 2 * kTilePts;

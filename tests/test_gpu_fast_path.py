@@ -172,7 +172,7 @@ def test_fast_path_index_adversarial(ctx, geom):
 
 
 # ----------------------------------------------------------------- template variants
-VARIANTS = [{"GV_FAST_KIND": "0"}, {"GV_COL_HOIST": "0"}, {"GV_FAST_KIND": "1"}, {"GV_FAST_KIND": "1", "GV_FAST_U": "1"},
+VARIANTS = [{"GV_FAST_KIND": "0"}, {"GV_FAST_KIND": "3"}, {"GV_FAST_KIND": "3", "GV_COL_HOIST": "1"}, {"GV_FAST_KIND": "1"}, {"GV_FAST_KIND": "1", "GV_FAST_U": "1"},
             {"GV_FAST_KIND": "1", "GV_TMA_HOIST": "1"}, {"GV_FAST_KIND": "2"},
             {"GV_FAST_KIND": "2", "GV_FAST_AGG": "0", "GV_FAST_U": "1"}, {"GV_FAST_KIND": "2", "GV_FAST_AGG": "1"},
             {"GV_FAST_KIND": "2", "GV_FAST_AGG": "2", "GV_FAST_U": "4"}, {"GV_L2_PERSIST": "0"}]
@@ -180,8 +180,9 @@ VARIANTS = [{"GV_FAST_KIND": "0"}, {"GV_COL_HOIST": "0"}, {"GV_FAST_KIND": "1"},
 
 @pytest.mark.parametrize("env", VARIANTS, ids=lambda e: ",".join(f"{k[3:]}={v}" for k, v in e.items()))
 def test_fast_path_kernel_variants(env):
-    """Every fast kernel (KIND 0 k_points_col: one thread per beam index across frames, run-length
-    binning in registers; 1 k_points_tma: persistent, bulk-copy fed, run slots in shared memory;
+    """Every fast kernel (KIND 0 k_points_pair: two adjacent points per thread on the packed f32x2
+    pipe where every frame offset and size is even, else k_points_col; 3 k_points_col: one thread per
+    beam index across frames, run-length binning in registers; 1 k_points_tma: persistent, bulk-copy fed, run slots in shared memory;
     2 k_points_fast: one CTA per tile, optional warp-level RED merging) and instantiation family
     on three frame layouts: arbitrary ragged sizes (LDG kernel:
     bulk copies need 4-point alignment), ragged sizes that are multiples of 4 (TMA kernel, partial
@@ -200,7 +201,7 @@ def test_fast_path_kernel_variants(env):
         rng = np.random.default_rng(5)
         Tc, Tb = synth.camera_extrinsics(1)[0], synth.T_base_lidar()
         per_frame = [synth.make_boxes(wl, frame=f, n=int(3 + 11 * f) % 65) for f in range(nframes)]
-        for align in (1, 4):
+        for align in (1, 2, 4):
             sizes = rng.integers(1, P // align + 1, nframes) * align
             sizes[1], sizes[2], sizes[3] = 0, align, 256 + align
             keep = np.concatenate([np.arange(f * P, f * P + sizes[f]) for f in range(nframes)])
