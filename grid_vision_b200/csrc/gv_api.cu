@@ -86,6 +86,7 @@ struct gv_ctx {
   bool multi_checked = false;  // ranks verified to share geometry + pose (gv_grid_finalize_multi)
   bool use_fast = true;  // $GV_NO_FAST=1 forces the generic k_points (A/B measurements)
   int fast_unroll = 2;   // $GV_FAST_U: points per thread per iteration of k_points_fast
+  int pair_minb = GV_PAIR_MINB;  // $GV_PAIR_MINB: CTAs per SM k_points_pair's register allocation aims at (3..6)
   bool col_hoist = false; // $GV_COL_HOIST=1: k_points_col keeps FastHot in registers (fewer instructions, 3 CTAs/SM)
   int fast_kind = 0;     // $GV_FAST_KIND: 0 k_points_pair where the layout allows it, else k_points_col (default),
                          // 1 k_points_tma, 2 k_points_fast, 3 k_points_col always
@@ -920,6 +921,8 @@ int gv_create(gv_ctx **out, int device)
   ctx->use_tma = std::getenv("GV_NO_TMA") == nullptr;
   if (const char *u = std::getenv("GV_FAST_KIND")) ctx->fast_kind = std::atoi(u);
   if (const char *u = std::getenv("GV_COL_HOIST")) ctx->col_hoist = std::atoi(u) != 0;
+  if (const char *u = std::getenv("GV_PAIR_MINB")) ctx->pair_minb = std::atoi(u);
+  if (ctx->pair_minb < 3 || ctx->pair_minb > 6) ctx->pair_minb = GV_PAIR_MINB;
   if (ctx->fast_kind != 1) ctx->use_tma = false;
   if (const char *u = std::getenv("GV_TMA_HOIST")) ctx->tma_hoist = std::atoi(u) != 0;
   if (const char *u = std::getenv("GV_L2_PERSIST")) ctx->l2_persist = std::atoi(u) != 0;
@@ -1923,7 +1926,7 @@ static int launch_points_col(gv_ctx *ctx, FastArgs &f, bool bounded, int frame0,
   const unsigned cols = ((max_pts + per_thread - 1) / per_thread + kThreads - 1) / kThreads;
   // enough CTAs for ~16 waves of 5 CTAs per SM, as few frame groups as that allows: the longer a
   // thread stays on its beam index, the more of the beam's repeats it merges before the RED
-  const unsigned want = (unsigned)ctx->num_sms * (f.pair ? (unsigned)GV_PAIR_MINB * 12u : 5u * 16u);
+  const unsigned want = (unsigned)ctx->num_sms * (f.pair ? (unsigned)ctx->pair_minb * 12u : 5u * 16u);
   unsigned groups = (want + cols - 1) / cols;
   if (groups > (unsigned)nframes) groups = (unsigned)nframes;
   if (groups < 1u) groups = 1u;
@@ -1953,15 +1956,25 @@ static int launch_points_col(gv_ctx *ctx, FastArgs &f, bool bounded, int frame0,
   if (f.pair) {
     PairArgs pa;
     fill_pair_args(f, pa);
-#define GV_PAIR_BL(ZZ)                                                                                \
+#define GV_PAIR_M(BB, LL, ZZ)                                                                         \
   do {                                                                                                \
-    if (bounded && lab) k_points_pair<true, true, ZZ><<<grid, kThreads, 0, ctx->stream>>>(f, pa);      \
-    else if (bounded) k_points_pair<true, false, ZZ><<<grid, kThreads, 0, ctx->stream>>>(f, pa);       \
-    else if (lab) k_points_pair<false, true, ZZ><<<grid, kThreads, 0, ctx->stream>>>(f, pa);           \
-    else k_points_pair<false, false, ZZ><<<grid, kThreads, 0, ctx->stream>>>(f, pa);                   \
+    switch (ctx->pair_minb) {                                                                         \
+    case 3: k_points_pair<BB, LL, ZZ, 3><<<grid, kThreads, 0, ctx->stream>>>(f, pa); break;            \
+    case 5: k_points_pair<BB, LL, ZZ, 5><<<grid, kThreads, 0, ctx->stream>>>(f, pa); break;            \
+    case 6: k_points_pair<BB, LL, ZZ, 6><<<grid, kThreads, 0, ctx->stream>>>(f, pa); break;            \
+    default: k_points_pair<BB, LL, ZZ, 4><<<grid, kThreads, 0, ctx->stream>>>(f, pa); break;           \
+    }                                                                                                 \
+  } while (0)
+#define GV_PAIR_BL(ZZ)                                \
+  do {                                                \
+    if (bounded && lab) GV_PAIR_M(true, true, ZZ);    \
+    else if (bounded) GV_PAIR_M(true, false, ZZ);     \
+    else if (lab) GV_PAIR_M(false, true, ZZ);         \
+    else GV_PAIR_M(false, false, ZZ);                 \
   } while (0)
     if (zg) GV_PAIR_BL(true);
     else GV_PAIR_BL(false);
+#undef GV_PAIR_M
 #undef GV_PAIR_BL
   } else if (zg) GV_COL_BL(true);
   else GV_COL_BL(false);

@@ -112,32 +112,49 @@ struct PairArgs {
   unsigned mask_bias;         // 0x4340 * (mask_tx + 1): see tile lookup
 };
 
-// label of one in-image lane: first certainly-containing candidate box in list order; a candidate
-// that is neither certainly outside nor certainly inside defers the point
+// Labels of both lanes.  mu = the candidate boxes of the lanes' image tiles (bit-reversed halves:
+// leading one = lowest box index), visited in list order; pend = the lane is certainly inside the
+// image and still unlabelled.  A candidate from the other lane's tile does not overlap this lane's
+// (1-px dilated) tile, so it tests "certainly outside" like any other miss.  The first candidate that
+// is not certainly outside ends the lane: certainly inside -> its label (ref :280-288, first box
+// wins), else the point is deferred.
 template <typename Boxes>
-__device__ __forceinline__ int label_lane(const Boxes &bsrc, unsigned long long m, float ql, float qh, float rl,
-                                          float rh, unsigned &def, unsigned bit)
+__device__ __forceinline__ void label_pair(const Boxes &bsrc, unsigned long long mu, bool pend0, bool pend1, f32x2 q,
+                                           f32x2 r, float eu, float ev, int &lab0, int &lab1, unsigned &def)
 {
-  int lab = -1;
-  unsigned mw = (unsigned)m;
+  const f32x2 ql = add2(q, bc2(-eu)), qh = add2(q, bc2(eu)), rl = add2(r, bc2(-ev)), rh = add2(r, bc2(ev));
+  const float ql0 = lo2(ql), ql1 = hi2(ql), qh0 = lo2(qh), qh1 = hi2(qh);
+  const float rl0 = lo2(rl), rl1 = hi2(rl), rh0 = lo2(rh), rh1 = hi2(rh);
+  unsigned mw = (unsigned)mu;
   unsigned base = 0;
 #pragma unroll 1
   for (;;) {
     if (mw == 0u) {
       if (base) break;
       base = 32u * 16u;
-      mw = (unsigned)(m >> 32);
+      mw = (unsigned)(mu >> 32);
       if (mw == 0u) break;
     }
-    const unsigned p = (unsigned)__clz((int)mw);  // bit-reversed halves: leading one = lowest box
+    const unsigned p = (unsigned)__clz((int)mw);
     mw &= ~(0x80000000u >> p);
     const float4 B = bsrc.box_at(base + 16u * p);
-    if (qh < B.x || ql > B.z || rh < B.y || rl > B.w) continue;  // certainly outside this box
-    if (ql >= B.x && qh <= B.z && rl >= B.y && rh <= B.w) lab = (int)((base >> 4) + p);  // first match
-    else def |= bit;
-    break;
+    const bool o0 = !pend0 | (qh0 < B.x) | (ql0 > B.z) | (rh0 < B.y) | (rl0 > B.w);  // certainly outside this box
+    const bool o1 = !pend1 | (qh1 < B.x) | (ql1 > B.z) | (rh1 < B.y) | (rl1 > B.w);
+    if (!(o0 & o1)) {
+      const int id = (int)((base >> 4) + p);
+      if (!o0) {
+        if ((ql0 >= B.x) & (qh0 <= B.z) & (rl0 >= B.y) & (rh0 <= B.w)) lab0 = id;
+        else def |= 1u;
+        pend0 = false;
+      }
+      if (!o1) {
+        if ((ql1 >= B.x) & (qh1 <= B.z) & (rl1 >= B.y) & (rh1 <= B.w)) lab1 = id;
+        else def |= 2u;
+        pend1 = false;
+      }
+      if (!(pend0 | pend1)) break;
+    }
   }
-  return lab;
 }
 
 // end cell of one lane whose certified index did not say "inside" (same code as fast_point)
@@ -169,24 +186,26 @@ __device__ __forceinline__ void offmap_lane(const FastArgs &a, float bx, float b
 }
 
 // run-length binning of one lane (see k_points_col): (cell, beams | hits << 16) in two registers
-__device__ __forceinline__ void run_bin_reg(unsigned long long *ends, int &run_cell, unsigned &run, int lin, unsigned hit)
+__device__ __forceinline__ void run_bin_reg(unsigned long long *ends, int &run_cell, unsigned &run, int lin, bool valid,
+                                            bool hit)
 {
-  if (lin != run_cell) {
-    if (run) atomicAdd(ends + run_cell, ((unsigned long long)(run >> 16) << 32) | (run & 0xffffu));
+  const bool changed = valid & (lin != run_cell);
+  if (changed & (run != 0u)) atomicAdd(ends + run_cell, ((unsigned long long)(run >> 16) << 32) | (run & 0xffffu));
+  if (changed) {
     run_cell = lin;
     run = 0u;
   }
-  run += hit ? 0x10001u : 1u;
+  if (valid) run += hit ? 0x10001u : 1u;
 }
 
 #ifndef GV_PAIR_MINB
-#define GV_PAIR_MINB 3
+#define GV_PAIR_MINB 5  // default CTAs per SM the register allocation aims at ($GV_PAIR_MINB at run time: 3..6)
 #endif
 
 // grid = (pair-column blocks, frame groups); a.frames_per_cta <= min(kColFrames, 32767) keeps the
 // 16-bit run counters exact
-template <bool BOUNDED, bool LAB, bool ZGATE>
-__global__ void __launch_bounds__(kThreads, GV_PAIR_MINB) k_points_pair(const __grid_constant__ FastArgs a,
+template <bool BOUNDED, bool LAB, bool ZGATE, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) k_points_pair(const __grid_constant__ FastArgs a,
                                                                         const __grid_constant__ PairArgs pa)
 {
   __shared__ uint4 s_rec[kColFrames + 1];  // {element offset relative to the group's first frame, points, first box, -}
@@ -216,13 +235,14 @@ __global__ void __launch_bounds__(kThreads, GV_PAIR_MINB) k_points_pair(const __
   int16_t *lb = LAB ? a.labels + off0 + idx : nullptr;
   unsigned fcur = (unsigned)f0;
   unsigned idx_r = idx;
+  unsigned sa_k = (unsigned)__cvta_generic_to_shared(s_rec);  // this frame's record
+  const unsigned sa_end = sa_k + 16u * (unsigned)nf;
   // opaque to the optimiser: otherwise these loop invariants are re-derived from the parameter
   // block and the special registers inside the loop (a dozen instructions per iteration)
-  asm volatile("" : "+l"(xb), "+l"(yb), "+l"(zb), "+l"(lb), "+r"(idx_r));
+  asm volatile("" : "+l"(xb), "+l"(yb), "+l"(zb), "+l"(lb), "+r"(idx_r), "+r"(sa_k));
   const f32x2 one = bc2(pa.one);
   f32x2 nx = 0ull, ny = 0ull, nz = 0ull;
-  uint4 rc = s_rec[0];
-  if (idx_r < rc.y) {
+  if (idx_r < first.z) {
     nx = __ldcs(reinterpret_cast<const unsigned long long *>(xb));
     ny = __ldcs(reinterpret_cast<const unsigned long long *>(yb));
     nz = __ldcs(reinterpret_cast<const unsigned long long *>(zb));
@@ -230,14 +250,16 @@ __global__ void __launch_bounds__(kThreads, GV_PAIR_MINB) k_points_pair(const __
   int cell0 = -1, cell1 = -1;
   unsigned run0 = 0u, run1 = 0u;
 #pragma unroll 1
-  for (int k = 0; k < nf; ++k, ++fcur) {
-    const uint4 rcur = rc;
-    rc = s_rec[k + 1];  // the next frame's record (entry nf: an empty frame)
+  for (; sa_k != sa_end; sa_k += 16u, ++fcur) {
+    uint4 rcur;
+    uint2 rnxt;  // the next frame's {offset, points} (entry nf: an empty frame)
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(rcur.x), "=r"(rcur.y), "=r"(rcur.z), "=r"(rcur.w) : "r"(sa_k));
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+16];" : "=r"(rnxt.x), "=r"(rnxt.y) : "r"(sa_k));
     const f32x2 px = nx, py = ny, pz = nz;
-    if (idx_r < rc.y) {  // the next frame's pair: in flight while this one is processed
-      nx = __ldcs(reinterpret_cast<const unsigned long long *>(xb + rc.x));
-      ny = __ldcs(reinterpret_cast<const unsigned long long *>(yb + rc.x));
-      nz = __ldcs(reinterpret_cast<const unsigned long long *>(zb + rc.x));
+    if (idx_r < rnxt.y) {  // the next frame's pair: in flight while this one is processed
+      nx = __ldcs(reinterpret_cast<const unsigned long long *>(xb + rnxt.x));
+      ny = __ldcs(reinterpret_cast<const unsigned long long *>(yb + rnxt.x));
+      nz = __ldcs(reinterpret_cast<const unsigned long long *>(zb + rnxt.x));
     }
     if (!(idx_r < rcur.y)) continue;
 
@@ -254,8 +276,12 @@ __global__ void __launch_bounds__(kThreads, GV_PAIR_MINB) k_points_pair(const __
     }
     // With |T| < 1e6 (host-checked) every transformed coordinate of an ok lane is finite (< 3.1e15).
 
-    // ---------------- camera: depth row first
+    // ---------------- camera: depth row first.  Ends with the image-tile mask loads in flight; the
+    // box tests that consume them run after the base-frame block (label_pair below).
     int lab0 = -1, lab1 = -1;
+    bool in0 = false, in1 = false;
+    f32x2 q = 0ull, r = 0ull;
+    unsigned long long cm0 = 0ull, cm1 = 0ull;
     {
       const f32x2 Z = se3_row2(h.Tcz, px, py, pz, one);
       const float Z0 = lo2(Z), Z1 = hi2(Z);
@@ -267,11 +293,12 @@ __global__ void __launch_bounds__(kThreads, GV_PAIR_MINB) k_points_pair(const __
         //   twice that (fast_point).  Inside or near the image |q| <= W + 1, so the constant
         //   pa.eu >= E(q) there; the image test itself uses thresholds derived from E(q) on the host.
         const f32x2 rz = pk2(rcp_approx(Z0), rcp_approx(Z1));
-        const f32x2 q = fma2(bc2(w.fx), mul2(X, rz), bc2(w.cx)), r = fma2(bc2(w.fy), mul2(Y, rz), bc2(w.cy));
+        q = fma2(bc2(w.fx), mul2(X, rz), bc2(w.cx));
+        r = fma2(bc2(w.fy), mul2(Y, rz), bc2(w.cy));
         const f32x2 dq = add2(q, bc2(-pa.half_w)), dr = add2(r, bc2(-pa.half_h));
         const float aq0 = fabsf(lo2(dq)), aq1 = fabsf(hi2(dq)), ar0 = fabsf(lo2(dr)), ar1 = fabsf(hi2(dr));
-        const bool in0 = fr0 & (aq0 < pa.ain_u) & (ar0 < pa.ain_v);  // certainly inside the image (:276)
-        const bool in1 = fr1 & (aq1 < pa.ain_u) & (ar1 < pa.ain_v);
+        in0 = fr0 & (aq0 < pa.ain_u) & (ar0 < pa.ain_v);  // certainly inside the image (:276)
+        in1 = fr1 & (aq1 < pa.ain_u) & (ar1 < pa.ain_v);
         // neither certainly inside nor certainly outside: too close to an image edge to call
         if (fr0 & !in0 & !((aq0 > pa.aout_u) | (ar0 > pa.aout_v))) def |= 1u;
         if (fr1 & !in1 & !((aq1 > pa.aout_u) | (ar1 > pa.aout_v))) def |= 2u;
@@ -279,19 +306,13 @@ __global__ void __launch_bounds__(kThreads, GV_PAIR_MINB) k_points_pair(const __
           // image tile: (q / S + 192) has ulp 2^-16, so bits >> 16 = 0x4340 + floor(q / S) up to
           // a rounding of 2^-16 tiles, which the 1-px dilation of the tile masks covers
           const f32x2 tu = fma2(q, bc2(pa.inv_tile), bc2(192.0f)), tv = fma2(r, bc2(pa.inv_tile), bc2(192.0f));
-          const f32x2 ql = add2(q, bc2(-pa.eu)), qh = add2(q, bc2(pa.eu));
-          const f32x2 rl = add2(r, bc2(-pa.ev)), rh = add2(r, bc2(pa.ev));
-          const GmemBoxes bsrc{a.boxes + rcur.z, a.masks + (size_t)fcur * a.mask_stride};
-          if (in0) {
-            const unsigned ti = (__float_as_uint(lo2(tv)) >> 16) * (unsigned)a.mask_tx +
-                                (__float_as_uint(lo2(tu)) >> 16) - pa.mask_bias;
-            lab0 = label_lane(bsrc, bsrc.mask_word(ti), lo2(ql), lo2(qh), lo2(rl), lo2(rh), def, 1u);
-          }
-          if (in1) {
-            const unsigned ti = (__float_as_uint(hi2(tv)) >> 16) * (unsigned)a.mask_tx +
-                                (__float_as_uint(hi2(tu)) >> 16) - pa.mask_bias;
-            lab1 = label_lane(bsrc, bsrc.mask_word(ti), hi2(ql), hi2(qh), hi2(rl), hi2(rh), def, 2u);
-          }
+          const unsigned long long *mrow = a.masks + (size_t)fcur * a.mask_stride;
+          if (in0)
+            cm0 = __ldg(mrow + ((__float_as_uint(lo2(tv)) >> 16) * (unsigned)a.mask_tx +
+                                (__float_as_uint(lo2(tu)) >> 16) - pa.mask_bias));
+          if (in1)
+            cm1 = __ldg(mrow + ((__float_as_uint(hi2(tv)) >> 16) * (unsigned)a.mask_tx +
+                                (__float_as_uint(hi2(tu)) >> 16) - pa.mask_bias));
         }
       }
     }
@@ -335,6 +356,9 @@ __global__ void __launch_bounds__(kThreads, GV_PAIR_MINB) k_points_pair(const __
         if (!ins1 & ok1) offmap_lane(a, bx1, by1, tx1, ty1, wok1, lin1, def, 2u);
       }
     }
+    // ---------------- labels (the masks have had the whole base-frame block to arrive)
+    if (in0 | in1)
+      label_pair(GmemBoxes{a.boxes + rcur.z, nullptr}, cm0 | cm1, in0, in1, q, r, pa.eu, pa.ev, lab0, lab1, def);
     bool hit0 = ins0 & !cap0 & (lab0 >= h.lab_min), hit1 = ins1 & !cap1 & (lab1 >= h.lab_min);
     if (ZGATE) {
       const f32x2 bz = se3_row2(a.Tbz, px, py, pz, one);
@@ -343,8 +367,8 @@ __global__ void __launch_bounds__(kThreads, GV_PAIR_MINB) k_points_pair(const __
     }
     // labels of the pair in one streaming store (a deferred lane's half is rewritten by k_points_deferred)
     if (LAB) __stcs(reinterpret_cast<unsigned *>(lb + rcur.x), ((unsigned)lab0 & 0xffffu) | ((unsigned)lab1 << 16));
-    if (ok0 & !(def & 1u)) run_bin_reg(a.ends, cell0, run0, lin0, hit0 ? 1u : 0u);
-    if (ok1 & !(def & 2u)) run_bin_reg(a.ends, cell1, run1, lin1, hit1 ? 1u : 0u);
+    run_bin_reg(a.ends, cell0, run0, lin0, ok0 & !(def & 1u), hit0);
+    run_bin_reg(a.ends, cell1, run1, lin1, ok1 & !(def & 2u), hit1);
     if (def) atomicOr(a.defer_bits + (size_t)fcur * a.defer_stride + (idx_r >> 5), def << (idx_r & 31u));
   }
   if (run0) atomicAdd(a.ends + cell0, ((unsigned long long)(run0 >> 16) << 32) | (run0 & 0xffffu));
