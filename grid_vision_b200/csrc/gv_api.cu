@@ -1897,6 +1897,21 @@ static void fill_pair_args(const FastArgs &f, PairArgs &p)
   memset(&p, 0, sizeof(p));
   p.one = 1.0f;
   const FastWarm &w = f.warm;
+  const FastHot &h = f.hot;
+  for (int i = 0; i < 4; ++i) {
+    p.Tcz[i] = h.Tcz[i];
+    p.Tcx[i] = w.Tcxy[i];
+    p.Tcy[i] = w.Tcxy[4 + i];
+    p.Tbx[i] = h.Tb[i];
+    p.Tby[i] = h.Tb[4 + i];
+  }
+  p.fx = w.fx; p.fy = w.fy; p.cx = w.cx; p.cy = w.cy;
+  p.oxf = h.oxf; p.oyf = h.oyf; p.noxf = -h.oxf; p.noyf = -h.oyf;
+  p.rmax2f = h.rmax2f; p.rmaxf = w.rmaxf;
+  p.nires = h.nires; p.Cx = h.Cx; p.Cy = h.Cy;
+  p.kb8 = h.kb8; p.nx = h.nx; p.klim_x16 = h.klim_x16; p.klim_y16 = h.klim_y16;
+  p.lab_min = h.lab_min;
+  p.defer_stride = f.defer_stride;
   const double e6 = w.e6, slack = 1.0 + 4.76837158203125e-07;  // 1 + 2^-21
   struct Axis { double W, e0; float *half, *ain, *aout, *e; };
   Axis ax[2] = {{(double)w.Wf, (double)w.e0u, &p.half_w, &p.ain_u, &p.aout_u, &p.eu},
@@ -1912,6 +1927,8 @@ static void fill_pair_args(const FastArgs &f, PairArgs &p)
     *a.aout = std::nextafterf((float)(((a.W + a.e0) / (1.0 - e6) - half) * slack), INFINITY);
   }
   p.inv_tile = 1.0f / (float)(1 << f.mask_shift);
+  p.mask_tx = (unsigned)f.mask_tx;
+  p.mask_stride = (unsigned)f.mask_stride;
   p.mask_bias = 0x4340u * (unsigned)(f.mask_tx + 1);
 }
 
@@ -2197,7 +2214,9 @@ static int process_batch_impl(gv_ctx *ctx, const float *px, const float *py, con
     fa.defer_stride = defer_stride;
     fa.col_mode = col ? 1 : 0;
     // k_points_pair: 64-bit point loads and 32-bit label stores at even point indices
-    fa.pair = col && ctx->fast_kind == 0 && ctx->c_pair_ok &&
+    fa.pair = col && ctx->fast_kind == 0 && ctx->c_pair_ok && foff[nframes] < 4294967295ull &&
+              (unsigned long long)nframes * (unsigned)a.mask_stride < 4000000000ull &&
+              (unsigned long long)nframes * defer_stride < 4000000000ull &&
               ((((uintptr_t)d_x | (uintptr_t)d_y | (uintptr_t)d_z) & 7u) == 0) && (((uintptr_t)d_lab & 3u) == 0);
     // bulk copies need 16-byte aligned sources and sizes: plane pointers aligned, every frame
     // boundary (hence every tile start and size) a multiple of 4 points

@@ -101,15 +101,27 @@ __device__ __forceinline__ f32x2 div_rn_inrange2(f32x2 a, f32x2 b)
   return fma2(r, y1, q0);
 }
 
-// Parameters of k_points_pair beyond FastArgs (filled by fill_pair_args)
-struct PairArgs {
-  float one;                  // 1.0f, opaque to ptxas (see mad2)
-  float half_w, half_h;       // image centre: the image test is |q - W/2| against a threshold
-  float ain_u, ain_v;         // |q - W/2| <  ain  => certainly 0 <= u < W
-  float aout_u, aout_v;       // |q - W/2| >  aout => certainly u < 0 or u >= W
-  float eu, ev;               // E(q) for any |q| <= W + 1: the interval of the box tests
-  float inv_tile;             // 2^-mask_shift
-  unsigned mask_bias;         // 0x4340 * (mask_tx + 1): see tile lookup
+// Hot parameters of k_points_pair, in 16-byte rows in the order the loop reads them (so that one
+// 128-bit constant load brings a whole row into uniform registers); filled by fill_pair_args
+struct __align__(16) PairArgs {
+  float Tcz[4];                               // camera extrinsic, depth row (R1)
+  float Tcx[4], Tcy[4];                       // camera extrinsic rows x, y
+  float fx, fy, cx, cy;                       // certified R3
+  float half_w, half_h, ain_u, ain_v;         // |q - W/2| <  ain  => certainly 0 <= u < W
+  float aout_u, aout_v, eu, ev;               // |q - W/2| >  aout => certainly outside; eu >= E(q) for |q| <= W + 1
+  float inv_tile;                             // 2^-mask_shift
+  unsigned mask_bias;                         // 0x4340 * (mask_tx + 1): see the tile lookup
+  unsigned mask_tx, mask_stride;
+  float Tbx[4], Tby[4];                       // base transform rows x, y (X1)
+  float noxf, noyf, rmax2f, rmaxf;            // -origin; rmax2f = +inf when the range cap is disabled
+  float oxf, oyf, one, pad0;                  // one = 1.0f, opaque to ptxas (see mad2)
+  double nires, Cx;                           // index FMA (fast_point)
+  double Cy;
+  unsigned kb8;
+  int nx;
+  unsigned klim_x16, klim_y16;
+  int lab_min;
+  unsigned defer_stride;
 };
 
 // Labels of both lanes.  mu = the candidate boxes of the lanes' image tiles (bit-reversed halves:
@@ -185,70 +197,192 @@ __device__ __forceinline__ void offmap_lane(const FastArgs &a, float bx, float b
   }
 }
 
-// run-length binning of one lane (see k_points_col): (cell, beams | hits << 16) in two registers
-__device__ __forceinline__ void run_bin_reg(unsigned long long *ends, int &run_cell, unsigned &run, int lin, bool valid,
-                                            bool hit)
-{
-  const bool changed = valid & (lin != run_cell);
-  if (changed & (run != 0u)) atomicAdd(ends + run_cell, ((unsigned long long)(run >> 16) << 32) | (run & 0xffffu));
-  if (changed) {
-    run_cell = lin;
-    run = 0u;
-  }
-  if (valid) run += hit ? 0x10001u : 1u;
-}
-
 #ifndef GV_PAIR_MINB
 #define GV_PAIR_MINB 5  // default CTAs per SM the register allocation aims at ($GV_PAIR_MINB at run time: 3..6)
 #endif
 
+struct PairRuns {  // run-length binning state of the two lanes: (cell, beams | hits << 16)
+  int cell0, cell1;
+  unsigned run0, run1;
+};
+
+// the beam's end cell differs from the open run: flush the run, open a new one
+__device__ __forceinline__ void run_flush_reg(unsigned long long *ends, int &run_cell, unsigned &run, int lin, bool valid)
+{
+  if (valid & (lin != run_cell)) {
+    if (run) atomicAdd(ends + run_cell, ((unsigned long long)(run >> 16) << 32) | (run & 0xffffu));
+    run_cell = lin;
+    run = 0u;
+  }
+}
+
+// One pair of points: label store, deferral bits, run-length bins.  rcur = the frame's record.
+template <bool BOUNDED, bool LAB, bool ZGATE>
+__device__ __forceinline__ void pair_body(const FastArgs &a, const PairArgs &pa, const f32x2 one, const unsigned idx,
+                                          const unsigned fcur, const uint4 rcur, const f32x2 px, const f32x2 py,
+                                          const f32x2 pz, PairRuns &st)
+{
+  // A point with a non-finite or huge coordinate is not tested up front: it keeps flowing, and
+  // IEEE arithmetic flags it.  0 * NaN = 0 * Inf = NaN, so a NaN or Inf coordinate makes EVERY
+  // SE(3) row non-finite whatever the matrix: the depth test is false (no label, ref :264), r2
+  // below is NaN or +Inf.  r2 = NaN drops the beam (X1); r2 >= 1e30 (Inf, or a finite coordinate
+  // large enough to threaten overflow: |T| < 1e6 is host-checked, so r2 < 1e30 bounds |x|, |y| of
+  // the base frame) defers the point.  A huge z alone leaves r2 small; it can only make the
+  // camera rows overflow, which turns q or r into Inf/NaN and fails both image tests: deferred.
+  unsigned def = 0u;  // bit 0 / 1: the even / odd point is deferred to k_points_deferred
+
+  // ---------------- camera: depth row first.  Ends with the image-tile mask loads in flight; the
+  // box tests that consume them run after the base-frame block (label_pair below).
+  int lab0 = -1, lab1 = -1;
+  bool in0 = false, in1 = false;
+  f32x2 q = 0ull, r = 0ull;
+  unsigned long long cm0 = 0ull, cm1 = 0ull;
+  {
+    const f32x2 Z = se3_row2(pa.Tcz, px, py, pz, one);
+    const float Z0 = lo2(Z), Z1 = hi2(Z);
+    const bool fr0 = Z0 > 0.001f, fr1 = Z1 > 0.001f;  // ref :264 (NaN: false)
+    if (fr0 | fr1) {
+      const f32x2 X = se3_row2(pa.Tcx, px, py, pz, one), Y = se3_row2(pa.Tcy, px, py, pz, one);
+      // certified projection: q = fx*(X/Z) + cx in binary32 with rcp.approx (1 ulp):
+      //   |q - u_ref| <= 2^-24 (5|u| + 3|cx|), and E(q) = 2^-22 (6|q| + 1.5|cx| + 1) is at least
+      //   twice that (fast_point).  Inside or near the image |q| <= W + 1, so the constant
+      //   pa.eu >= E(q) there; the image test itself uses thresholds derived from E(q) on the host.
+      const f32x2 rz = pk2(rcp_approx(Z0), rcp_approx(Z1));
+      q = fma2(bc2(pa.fx), mul2(X, rz), bc2(pa.cx));
+      r = fma2(bc2(pa.fy), mul2(Y, rz), bc2(pa.cy));
+      const f32x2 dq = add2(q, bc2(-pa.half_w)), dr = add2(r, bc2(-pa.half_h));
+      const float aq0 = fabsf(lo2(dq)), aq1 = fabsf(hi2(dq)), ar0 = fabsf(lo2(dr)), ar1 = fabsf(hi2(dr));
+      in0 = fr0 & (aq0 < pa.ain_u) & (ar0 < pa.ain_v);  // certainly inside the image (:276)
+      in1 = fr1 & (aq1 < pa.ain_u) & (ar1 < pa.ain_v);
+      // neither certainly inside nor certainly outside: too close to an image edge to call
+      const bool e0 = fr0 & !in0 & !((aq0 > pa.aout_u) | (ar0 > pa.aout_v));
+      const bool e1 = fr1 & !in1 & !((aq1 > pa.aout_u) | (ar1 > pa.aout_v));
+      def |= (e0 ? 1u : 0u) | (e1 ? 2u : 0u);
+      if (in0 | in1) {
+        // image tile: (q / S + 192) has ulp 2^-16, so bits >> 16 = 0x4340 + floor(q / S) up to
+        // a rounding of 2^-16 tiles, which the 1-px dilation of the tile masks covers
+        const f32x2 tu = fma2(q, bc2(pa.inv_tile), bc2(192.0f)), tv = fma2(r, bc2(pa.inv_tile), bc2(192.0f));
+        if (in0)
+          cm0 = __ldg(a.masks + ((__float_as_uint(lo2(tv)) >> 16) * pa.mask_tx + (__float_as_uint(lo2(tu)) >> 16) + rcur.w));
+        if (in1)
+          cm1 = __ldg(a.masks + ((__float_as_uint(hi2(tv)) >> 16) * pa.mask_tx + (__float_as_uint(hi2(tu)) >> 16) + rcur.w));
+      }
+    }
+  }
+
+  // ---------------- base frame: end cell (oracle gvo_accumulate, per-point body)
+  f32x2 bx = se3_row2(pa.Tbx, px, py, pz, one), by = se3_row2(pa.Tby, px, py, pz, one);
+  bool cap0, cap1, ok0, ok1;
+  {
+    const f32x2 dx = add2(bx, bc2(pa.noxf)), dy = add2(by, bc2(pa.noyf));
+    const f32x2 r2 = fma2(mul2(dx, dx), one, mul2(dy, dy));
+    ok0 = lo2(r2) < 1.0e30f;
+    ok1 = hi2(r2) < 1.0e30f;
+    def |= (lo2(r2) >= 1.0e30f ? 1u : 0u) | (hi2(r2) >= 1.0e30f ? 2u : 0u);
+    cap0 = lo2(r2) > pa.rmax2f;
+    cap1 = hi2(r2) > pa.rmax2f;
+    if (cap0 | cap1) {  // beyond the mapping range: free-space-only beam shortened to r_max
+      const f32x2 sf = div_rn_inrange2(bc2(pa.rmaxf), sqrt_rn_inrange2(r2));
+      const f32x2 cx = mad2(sf, dx, bc2(pa.oxf), one), cy = mad2(sf, dy, bc2(pa.oyf), one);
+      bx = pk2(cap0 ? lo2(cx) : lo2(bx), cap1 ? hi2(cx) : hi2(bx));
+      by = pk2(cap0 ? lo2(cy) : lo2(by), cap1 ? hi2(cy) : hi2(by));
+    }
+  }
+  // certified index (fast_point): low word of fma((double)b, -1/res, C) = 16.16 index coordinate
+  int lin0, lin1;
+  bool ins0, ins1;
+  {
+    const float bx0 = lo2(bx), bx1 = hi2(bx), by0 = lo2(by), by1 = hi2(by);
+    const double rx0 = fma((double)bx0, pa.nires, pa.Cx), ry0 = fma((double)by0, pa.nires, pa.Cy);
+    const double rx1 = fma((double)bx1, pa.nires, pa.Cx), ry1 = fma((double)by1, pa.nires, pa.Cy);
+    const unsigned tx0 = (unsigned)__double2loint(rx0) - pa.kb8, ty0 = (unsigned)__double2loint(ry0) - pa.kb8;
+    const unsigned tx1 = (unsigned)__double2loint(rx1) - pa.kb8, ty1 = (unsigned)__double2loint(ry1) - pa.kb8;
+    bool wok0 = true, wok1 = true;
+    if (!BOUNDED) {
+      wok0 = ((unsigned)__double2hiint(rx0) == a.hi0) & ((unsigned)__double2hiint(ry0) == a.hi0);
+      wok1 = ((unsigned)__double2hiint(rx1) == a.hi0) & ((unsigned)__double2hiint(ry1) == a.hi0);
+    }
+    ins0 = wok0 & (tx0 < pa.klim_x16) & (ty0 < pa.klim_y16) & (max(tx0 & 0xffffu, ty0 & 0xffffu) < 0xfff0u);
+    ins1 = wok1 & (tx1 < pa.klim_x16) & (ty1 < pa.klim_y16) & (max(tx1 & 0xffffu, ty1 & 0xffffu) < 0xfff0u);
+    lin0 = (int)(tx0 >> 16) + (int)(ty0 >> 16) * pa.nx;
+    lin1 = (int)(tx1 >> 16) + (int)(ty1 >> 16) * pa.nx;
+    // a lane without a usable point must not drag the warp into the off-map code
+    if (!((ins0 | !ok0) & (ins1 | !ok1))) {
+      if (!ins0 & ok0) offmap_lane(a, bx0, by0, tx0, ty0, wok0, lin0, def, 1u);
+      if (!ins1 & ok1) offmap_lane(a, bx1, by1, tx1, ty1, wok1, lin1, def, 2u);
+    }
+  }
+  // ---------------- labels (the masks have had the whole base-frame block to arrive)
+  if (in0 | in1)
+    label_pair(GmemBoxes{a.boxes + rcur.z, nullptr}, cm0 | cm1, in0, in1, q, r, pa.eu, pa.ev, lab0, lab1, def);
+  bool hit0 = ins0 & !cap0 & (lab0 >= pa.lab_min), hit1 = ins1 & !cap1 & (lab1 >= pa.lab_min);
+  if (ZGATE) {
+    const f32x2 bz = se3_row2(a.Tbz, px, py, pz, one);
+    hit0 &= (lo2(bz) >= a.z_min) & (lo2(bz) <= a.z_max);
+    hit1 &= (hi2(bz) >= a.z_min) & (hi2(bz) <= a.z_max);
+  }
+  // labels of the pair in one streaming store (a deferred lane's half is rewritten by k_points_deferred)
+  if (LAB) __stcs(reinterpret_cast<unsigned *>(a.labels + (rcur.x + idx)), ((unsigned)lab0 & 0xffffu) | ((unsigned)lab1 << 16));
+  {
+    const bool v0 = ok0 & !(def & 1u), v1 = ok1 & !(def & 2u);
+    // common case first: both beams end where this thread's previous beams ended
+    if ((v0 & (lin0 != st.cell0)) | (v1 & (lin1 != st.cell1))) {
+      run_flush_reg(a.ends, st.cell0, st.run0, lin0, v0);
+      run_flush_reg(a.ends, st.cell1, st.run1, lin1, v1);
+    }
+    st.run0 += v0 ? (hit0 ? 0x10001u : 1u) : 0u;
+    st.run1 += v1 ? (hit1 ? 0x10001u : 1u) : 0u;
+  }
+  if (def) atomicOr(a.defer_bits + (fcur * pa.defer_stride + (idx >> 5)), def << (idx & 31u));
+}
+
 // grid = (pair-column blocks, frame groups); a.frames_per_cta <= min(kColFrames, 32767) keeps the
-// 16-bit run counters exact
+// 16-bit run counters exact.  Every point index of the launch is below 2^32 (host-checked): the
+// loop carries ONE 32-bit element offset and takes the plane bases from the parameter block.
 template <bool BOUNDED, bool LAB, bool ZGATE, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) k_points_pair(const __grid_constant__ FastArgs a,
-                                                                        const __grid_constant__ PairArgs pa)
+                                                                const __grid_constant__ PairArgs pa)
 {
-  __shared__ uint4 s_rec[kColFrames + 1];  // {element offset relative to the group's first frame, points, first box, -}
-  const unsigned pidx = blockIdx.x * kThreads + threadIdx.x;
-  const unsigned idx = 2u * pidx;  // this thread's even point; idx + 1 is its odd point
+  __shared__ uint4 s_rec[kColFrames + 1];  // {element offset of the frame, points, first box, frame * mask_stride - mask_bias}
   const int f0 = a.frame0 + (int)blockIdx.y * a.frames_per_cta;
   int nf = a.frame0 + a.nframes - f0;
   if (nf > a.frames_per_cta) nf = a.frames_per_cta;
   if (nf <= 0) return;
-  const uint4 first = __ldg(a.frames + f0);
-  const unsigned long long off0 = ((unsigned long long)first.y << 32) | first.x;
   for (int k = threadIdx.x; k <= nf; k += kThreads) {
     uint4 r = make_uint4(0u, 0u, 0u, 0u);
     if (k < nf) {
       const uint4 g = __ldg(a.frames + f0 + k);
-      r.x = (unsigned)((((unsigned long long)g.y << 32) | g.x) - off0);  // < 2^32: host-checked
+      r.x = g.x;  // g.y == 0: host-checked
       r.y = g.z;
       r.z = g.w;
+      r.w = (unsigned)(f0 + k) * pa.mask_stride - pa.mask_bias;
     }
     s_rec[k] = r;  // entry nf: an empty frame (ends the prefetch chain)
   }
   __syncthreads();
-  const FastHot &h = a.hot;
-  const FastWarm &w = a.warm;
 
-  const float *xb = a.x + off0 + idx, *yb = a.y + off0 + idx, *zb = a.z + off0 + idx;
-  int16_t *lb = LAB ? a.labels + off0 + idx : nullptr;
+  unsigned idx = 2u * (blockIdx.x * kThreads + threadIdx.x);  // this thread's even point; idx + 1 is its odd point
   unsigned fcur = (unsigned)f0;
-  unsigned idx_r = idx;
   unsigned sa_k = (unsigned)__cvta_generic_to_shared(s_rec);  // this frame's record
   const unsigned sa_end = sa_k + 16u * (unsigned)nf;
-  // opaque to the optimiser: otherwise these loop invariants are re-derived from the parameter
-  // block and the special registers inside the loop (a dozen instructions per iteration)
-  asm volatile("" : "+l"(xb), "+l"(yb), "+l"(zb), "+l"(lb), "+r"(idx_r), "+r"(sa_k));
+  // opaque to the optimiser: otherwise these loop invariants are re-derived from the special
+  // registers inside the loop
+  asm volatile("" : "+r"(idx), "+r"(sa_k));
   const f32x2 one = bc2(pa.one);
+  PairRuns st{-1, -1, 0u, 0u};
   f32x2 nx = 0ull, ny = 0ull, nz = 0ull;
-  if (idx_r < first.z) {
-    nx = __ldcs(reinterpret_cast<const unsigned long long *>(xb));
-    ny = __ldcs(reinterpret_cast<const unsigned long long *>(yb));
-    nz = __ldcs(reinterpret_cast<const unsigned long long *>(zb));
+  {
+    uint2 r0;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r0.x), "=r"(r0.y) : "r"(sa_k));
+    if (idx < r0.y) {
+      const unsigned o = r0.x + idx;
+      nx = __ldcs(reinterpret_cast<const unsigned long long *>(a.x + o));
+      ny = __ldcs(reinterpret_cast<const unsigned long long *>(a.y + o));
+      nz = __ldcs(reinterpret_cast<const unsigned long long *>(a.z + o));
+    }
   }
-  int cell0 = -1, cell1 = -1;
-  unsigned run0 = 0u, run1 = 0u;
+  // (Two frames per trip with ping-pong point registers, to drop the six register copies of the
+  // software pipeline, was measured slower: under the 48-register budget the in-flight loads spill.)
 #pragma unroll 1
   for (; sa_k != sa_end; sa_k += 16u, ++fcur) {
     uint4 rcur;
@@ -256,123 +390,16 @@ __global__ void __launch_bounds__(kThreads, MINB) k_points_pair(const __grid_con
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(rcur.x), "=r"(rcur.y), "=r"(rcur.z), "=r"(rcur.w) : "r"(sa_k));
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+16];" : "=r"(rnxt.x), "=r"(rnxt.y) : "r"(sa_k));
     const f32x2 px = nx, py = ny, pz = nz;
-    if (idx_r < rnxt.y) {  // the next frame's pair: in flight while this one is processed
-      nx = __ldcs(reinterpret_cast<const unsigned long long *>(xb + rnxt.x));
-      ny = __ldcs(reinterpret_cast<const unsigned long long *>(yb + rnxt.x));
-      nz = __ldcs(reinterpret_cast<const unsigned long long *>(zb + rnxt.x));
+    if (idx < rnxt.y) {  // the next frame's pair: in flight while this one is processed
+      const unsigned o = rnxt.x + idx;
+      nx = __ldcs(reinterpret_cast<const unsigned long long *>(a.x + o));
+      ny = __ldcs(reinterpret_cast<const unsigned long long *>(a.y + o));
+      nz = __ldcs(reinterpret_cast<const unsigned long long *>(a.z + o));
     }
-    if (!(idx_r < rcur.y)) continue;
-
-    const float x0 = lo2(px), x1 = hi2(px), y0 = lo2(py), y1 = hi2(py), z0 = lo2(pz), z1 = hi2(pz);
-    // all three |v| < 1e9?  max.NaN propagates NaN, so NaN and Inf fail the compare.  A lane that
-    // fails keeps flowing (its values are garbage, every use below is masked by ok / def).
-    const float m0 = fmax3_nan_abs(x0, y0, z0), m1 = fmax3_nan_abs(x1, y1, z1);
-    const bool ok0 = m0 < 1.0e9f, ok1 = m1 < 1.0e9f;
-    unsigned def = 0u;  // bit 0 / 1: the even / odd point is deferred to k_points_deferred
-    if (!(ok0 & ok1)) {
-      // finite but huge: nothing is certified.  non-finite: no label (ref :264), beam dropped (X1)
-      if (!ok0 & (m0 < __int_as_float(0x7f800000))) def |= 1u;
-      if (!ok1 & (m1 < __int_as_float(0x7f800000))) def |= 2u;
-    }
-    // With |T| < 1e6 (host-checked) every transformed coordinate of an ok lane is finite (< 3.1e15).
-
-    // ---------------- camera: depth row first.  Ends with the image-tile mask loads in flight; the
-    // box tests that consume them run after the base-frame block (label_pair below).
-    int lab0 = -1, lab1 = -1;
-    bool in0 = false, in1 = false;
-    f32x2 q = 0ull, r = 0ull;
-    unsigned long long cm0 = 0ull, cm1 = 0ull;
-    {
-      const f32x2 Z = se3_row2(h.Tcz, px, py, pz, one);
-      const float Z0 = lo2(Z), Z1 = hi2(Z);
-      const bool fr0 = Z0 > 0.001f, fr1 = Z1 > 0.001f;  // ref :264 (NaN: false)
-      if (fr0 | fr1) {
-        const f32x2 X = se3_row2(w.Tcxy, px, py, pz, one), Y = se3_row2(w.Tcxy + 4, px, py, pz, one);
-        // certified projection: q = fx*(X/Z) + cx in binary32 with rcp.approx (1 ulp):
-        //   |q - u_ref| <= 2^-24 (5|u| + 3|cx|), and E(q) = 2^-22 (6|q| + 1.5|cx| + 1) is at least
-        //   twice that (fast_point).  Inside or near the image |q| <= W + 1, so the constant
-        //   pa.eu >= E(q) there; the image test itself uses thresholds derived from E(q) on the host.
-        const f32x2 rz = pk2(rcp_approx(Z0), rcp_approx(Z1));
-        q = fma2(bc2(w.fx), mul2(X, rz), bc2(w.cx));
-        r = fma2(bc2(w.fy), mul2(Y, rz), bc2(w.cy));
-        const f32x2 dq = add2(q, bc2(-pa.half_w)), dr = add2(r, bc2(-pa.half_h));
-        const float aq0 = fabsf(lo2(dq)), aq1 = fabsf(hi2(dq)), ar0 = fabsf(lo2(dr)), ar1 = fabsf(hi2(dr));
-        in0 = fr0 & (aq0 < pa.ain_u) & (ar0 < pa.ain_v);  // certainly inside the image (:276)
-        in1 = fr1 & (aq1 < pa.ain_u) & (ar1 < pa.ain_v);
-        // neither certainly inside nor certainly outside: too close to an image edge to call
-        if (fr0 & !in0 & !((aq0 > pa.aout_u) | (ar0 > pa.aout_v))) def |= 1u;
-        if (fr1 & !in1 & !((aq1 > pa.aout_u) | (ar1 > pa.aout_v))) def |= 2u;
-        if (in0 | in1) {
-          // image tile: (q / S + 192) has ulp 2^-16, so bits >> 16 = 0x4340 + floor(q / S) up to
-          // a rounding of 2^-16 tiles, which the 1-px dilation of the tile masks covers
-          const f32x2 tu = fma2(q, bc2(pa.inv_tile), bc2(192.0f)), tv = fma2(r, bc2(pa.inv_tile), bc2(192.0f));
-          const unsigned long long *mrow = a.masks + (size_t)fcur * a.mask_stride;
-          if (in0)
-            cm0 = __ldg(mrow + ((__float_as_uint(lo2(tv)) >> 16) * (unsigned)a.mask_tx +
-                                (__float_as_uint(lo2(tu)) >> 16) - pa.mask_bias));
-          if (in1)
-            cm1 = __ldg(mrow + ((__float_as_uint(hi2(tv)) >> 16) * (unsigned)a.mask_tx +
-                                (__float_as_uint(hi2(tu)) >> 16) - pa.mask_bias));
-        }
-      }
-    }
-
-    // ---------------- base frame: end cell (oracle gvo_accumulate, per-point body)
-    f32x2 bx = se3_row2(h.Tb, px, py, pz, one), by = se3_row2(h.Tb + 4, px, py, pz, one);
-    bool cap0, cap1;
-    {
-      const f32x2 dx = add2(bx, bc2(-h.oxf)), dy = add2(by, bc2(-h.oyf));
-      const f32x2 r2 = fma2(mul2(dx, dx), one, mul2(dy, dy));
-      cap0 = lo2(r2) > h.rmax2f;
-      cap1 = hi2(r2) > h.rmax2f;
-      if (cap0 | cap1) {  // beyond the mapping range: free-space-only beam shortened to r_max
-        const f32x2 sf = div_rn_inrange2(bc2(w.rmaxf), sqrt_rn_inrange2(r2));
-        const f32x2 cx = mad2(sf, dx, bc2(h.oxf), one), cy = mad2(sf, dy, bc2(h.oyf), one);
-        bx = pk2(cap0 ? lo2(cx) : lo2(bx), cap1 ? hi2(cx) : hi2(bx));
-        by = pk2(cap0 ? lo2(cy) : lo2(by), cap1 ? hi2(cy) : hi2(by));
-      }
-    }
-    // certified index (fast_point): low word of fma((double)b, -1/res, C) = 16.16 index coordinate
-    int lin0, lin1;
-    bool ins0, ins1;
-    {
-      const float bx0 = lo2(bx), bx1 = hi2(bx), by0 = lo2(by), by1 = hi2(by);
-      const double rx0 = fma((double)bx0, h.nires, h.Cx), ry0 = fma((double)by0, h.nires, h.Cy);
-      const double rx1 = fma((double)bx1, h.nires, h.Cx), ry1 = fma((double)by1, h.nires, h.Cy);
-      const unsigned tx0 = (unsigned)__double2loint(rx0) - h.kb8, ty0 = (unsigned)__double2loint(ry0) - h.kb8;
-      const unsigned tx1 = (unsigned)__double2loint(rx1) - h.kb8, ty1 = (unsigned)__double2loint(ry1) - h.kb8;
-      bool wok0 = true, wok1 = true;
-      if (!BOUNDED) {
-        wok0 = ((unsigned)__double2hiint(rx0) == a.hi0) & ((unsigned)__double2hiint(ry0) == a.hi0);
-        wok1 = ((unsigned)__double2hiint(rx1) == a.hi0) & ((unsigned)__double2hiint(ry1) == a.hi0);
-      }
-      ins0 = wok0 & (tx0 < h.klim_x16) & (ty0 < h.klim_y16) & (max(tx0 & 0xffffu, ty0 & 0xffffu) < 0xfff0u);
-      ins1 = wok1 & (tx1 < h.klim_x16) & (ty1 < h.klim_y16) & (max(tx1 & 0xffffu, ty1 & 0xffffu) < 0xfff0u);
-      lin0 = (int)(tx0 >> 16) + (int)(ty0 >> 16) * h.nx;
-      lin1 = (int)(tx1 >> 16) + (int)(ty1 >> 16) * h.nx;
-      // a lane without a usable point must not drag the warp into the off-map code
-      if (!((ins0 | !ok0) & (ins1 | !ok1))) {
-        if (!ins0 & ok0) offmap_lane(a, bx0, by0, tx0, ty0, wok0, lin0, def, 1u);
-        if (!ins1 & ok1) offmap_lane(a, bx1, by1, tx1, ty1, wok1, lin1, def, 2u);
-      }
-    }
-    // ---------------- labels (the masks have had the whole base-frame block to arrive)
-    if (in0 | in1)
-      label_pair(GmemBoxes{a.boxes + rcur.z, nullptr}, cm0 | cm1, in0, in1, q, r, pa.eu, pa.ev, lab0, lab1, def);
-    bool hit0 = ins0 & !cap0 & (lab0 >= h.lab_min), hit1 = ins1 & !cap1 & (lab1 >= h.lab_min);
-    if (ZGATE) {
-      const f32x2 bz = se3_row2(a.Tbz, px, py, pz, one);
-      hit0 &= (lo2(bz) >= a.z_min) & (lo2(bz) <= a.z_max);
-      hit1 &= (hi2(bz) >= a.z_min) & (hi2(bz) <= a.z_max);
-    }
-    // labels of the pair in one streaming store (a deferred lane's half is rewritten by k_points_deferred)
-    if (LAB) __stcs(reinterpret_cast<unsigned *>(lb + rcur.x), ((unsigned)lab0 & 0xffffu) | ((unsigned)lab1 << 16));
-    run_bin_reg(a.ends, cell0, run0, lin0, ok0 & !(def & 1u), hit0);
-    run_bin_reg(a.ends, cell1, run1, lin1, ok1 & !(def & 2u), hit1);
-    if (def) atomicOr(a.defer_bits + (size_t)fcur * a.defer_stride + (idx_r >> 5), def << (idx_r & 31u));
+    if (idx < rcur.y) pair_body<BOUNDED, LAB, ZGATE>(a, pa, one, idx, fcur, rcur, px, py, pz, st);
   }
-  if (run0) atomicAdd(a.ends + cell0, ((unsigned long long)(run0 >> 16) << 32) | (run0 & 0xffffu));
-  if (run1) atomicAdd(a.ends + cell1, ((unsigned long long)(run1 >> 16) << 32) | (run1 & 0xffffu));
+  if (st.run0) atomicAdd(a.ends + st.cell0, ((unsigned long long)(st.run0 >> 16) << 32) | (st.run0 & 0xffffu));
+  if (st.run1) atomicAdd(a.ends + st.cell1, ((unsigned long long)(st.run1 >> 16) << 32) | (st.run1 & 0xffffu));
 }
 
 }  // namespace gv
