@@ -62,6 +62,8 @@ struct gv_ctx {
   size_t ncells = 0;
   float *d_lo = nullptr, *d_occ = nullptr;
   int32_t *d_hit = nullptr, *d_miss = nullptr;
+  int32_t *d_missT = nullptr;  // transposed miss plane of the x-major lines (k_sweep_walk), all-zero between sweeps
+  double sweep_reach = 0.0;    // cells a beam binned since the last sweep can extend from the origin (inf: no range cap)
   // Two end-cell planes: beams are binned into d_ends (= d_ends_buf[ends_cur]) on the caller's
   // stream while the previous batch's plane is merged (raycast + [exchange] + finalise) on
   // merge_stream.  ev_merge_done[i] / merge_busy[i]: the merge that consumed plane i.
@@ -189,7 +191,9 @@ void stage_mark(gv_ctx *ctx, int i)
 void stage_collect(gv_ctx *ctx)
 {
   if (!ctx->timing || ctx->tev_n < 2) return;
-  cudaEventSynchronize(ctx->tev[ctx->tev_n - 1]);
+  // never block the host here (that would serialise the merge with the next batch's binning):
+  // a chain whose last event has not completed yet is simply not sampled
+  if (cudaEventQuery(ctx->tev[ctx->tev_n - 1]) != cudaSuccess) return;
   for (int i = 0; i + 1 < ctx->tev_n; ++i) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, ctx->tev[i], ctx->tev[i + 1]) == cudaSuccess) ctx->t_acc[i] += ms;
@@ -402,6 +406,8 @@ int set_bin_params(gv_ctx *ctx, const gv_accum_params *prm, BinDev *out)
   // specification (oracle gvo_beam_geom_init); host floats are IEEE binary32, no contraction
   out->rmaxf = (float)prm->r_max;
   out->rmax2f = out->rmaxf * out->rmaxf;
+  const double reach = out->cap ? std::ceil((double)out->rmaxf / ctx->g.res) + 4.0 : INFINITY;
+  if (reach > ctx->sweep_reach) ctx->sweep_reach = reach;
   return GV_OK;
 }
 
@@ -572,10 +578,28 @@ int raycast_flush_impl(gv_ctx *ctx, unsigned rank, unsigned world, bool p2p_gath
       d_bw, ctx->d_stats, ctx->peer_ends);
   GV_LAUNCH_CHECK();
   stage_mark(ctx, 3);
-  k_sweep_walk<<<nb, kThreads, 0, ctx->stream>>>(ctx->d_miss, ctx->d_sweep, ctx->d_list_count, d_bentry,
-                                                 d_bmi, d_bw, ctx->bin.sx, ctx->bin.sy, ctx->g.nx,
+  k_sweep_walk<<<nb, kThreads, 0, ctx->stream>>>(ctx->d_miss, ctx->d_missT, ctx->d_sweep, ctx->d_list_count, d_bentry,
+                                                 d_bmi, d_bw, ctx->bin.sx, ctx->bin.sy, ctx->g.nx, ctx->g.ny,
                                                  ctx->d_stats);
   GV_LAUNCH_CHECK();
+  {
+    // fold the x-major lines' transposed plane back: they stay within the range cap of the origin
+    int x0 = 0, y0 = 0, x1 = ctx->g.nx - 1, y1 = ctx->g.ny - 1;
+    // (multi-GPU: this rank also walks lines other ranks binned, under their own caps: whole map)
+    if (world == 1) {
+      if (ctx->sweep_reach < 1.0e9) {
+        const int R = (int)ctx->sweep_reach;
+        x0 = std::max(x0, ctx->bin.sx - R); x1 = std::min(x1, ctx->bin.sx + R);
+        y0 = std::max(y0, ctx->bin.sy - R); y1 = std::min(y1, ctx->bin.sy + R);
+      }
+    }
+    if (x1 >= x0 && y1 >= y0) {
+      const dim3 grid((unsigned)((x1 - x0) / 32 + 1), (unsigned)((y1 - y0) / 32 + 1));
+      k_miss_fold<<<grid, 256, 0, ctx->stream>>>(ctx->d_miss, ctx->d_missT, ctx->g.nx, ctx->g.ny, x0, y0, x1, y1);
+      GV_LAUNCH_CHECK();
+    }
+    ctx->sweep_reach = 0.0;
+  }
   stage_mark(ctx, 4);
   // multi-GPU, NCCL path: the plane holds every rank's (all-reduced) entries but this rank
   // walked only its own items: drop the rest.  (P2P: the owners cleared every rank's cells.)
@@ -741,6 +765,8 @@ void free_grid(gv_ctx *ctx)
   cudaFree(ctx->d_occ);
   cudaFree(ctx->d_hit);
   cudaFree(ctx->d_miss);
+  cudaFree(ctx->d_missT);
+  ctx->d_missT = nullptr;
   cudaFree(ctx->d_ends_buf[0]);
   cudaFree(ctx->d_ends_buf[1]);
   ctx->d_ends_buf[0] = ctx->d_ends_buf[1] = nullptr;
@@ -823,6 +849,8 @@ int grid_init_impl(gv_ctx *ctx, double length_x, double length_y, double res, do
   GV_CUDA(cudaMalloc(&ctx->d_occ, padded * sizeof(float)));
   GV_CUDA(cudaMalloc(&ctx->d_hit, padded * sizeof(int32_t)));
   GV_CUDA(cudaMalloc(&ctx->d_miss, padded * sizeof(int32_t)));
+  GV_CUDA(cudaMalloc(&ctx->d_missT, padded * sizeof(int32_t)));
+  GV_CUDA(cudaMemsetAsync(ctx->d_missT, 0, padded * sizeof(int32_t), ctx->stream));
   GV_CUDA(cudaMalloc(&ctx->d_ends_buf[0], padded * sizeof(unsigned long long)));
   GV_CUDA(cudaMalloc(&ctx->d_ends_buf[1], padded * sizeof(unsigned long long)));
   ctx->ends_cur = 0;

@@ -808,7 +808,7 @@ __global__ void __launch_bounds__(kThreads) k_label_scatter(const int16_t *__res
 //     ballot find the runs, and the run's weight is a difference of the warp prefix sum of w_e
 //     (computed once, the weights do not change along the walk): ONE RED per distinct cell.
 // The end cells themselves are settled too (hit += high word, miss += low - high) and the ends
-// plane is cleared.  Multi-GPU: span i belongs to rank i % world (the table is identical on
+// plane is cleared.  Multi-GPU: span i belongs to rank (i - i / world) % world (the table is identical on
 // every rank).  LineIterator restatement: oracle gvo_line_init / gvo_line_step.
 // ----------------------------------------------------------------------------------
 // Peer-memory views of one plane on every rank (cudaIpc-mapped, NVLink P2P); p[rank] is local.
@@ -824,7 +824,8 @@ struct SweepEntry {
   int m0, m1;  // inclusive range of the minor coordinate (absolute index), clipped to the map
 };
 
-// Scheduling: the span list is sorted by decreasing D; rank r owns spans r, r + world, ... and
+// Scheduling: the span list is sorted by decreasing D; rank r owns one span of every round of `world`
+// spans (rotating, see k_sweep_compact) and
 // warps pull work through an atomic counter, longest first.  (Measured: static round-robin is
 // 20 % slower — most spans carry no beams and the busy ones cluster — and cutting lines into
 // segments for more parallelism costs more in set-up than it gains.)
@@ -886,7 +887,11 @@ __global__ void __launch_bounds__(kThreads) k_sweep_compact(
     __syncthreads();  // s_item / s_cnt of the previous span are no longer read
     if (threadIdx.x == 0) s_item = atomicAdd(counters, 1u);
     __syncthreads();
-    const unsigned long long item64 = (unsigned long long)s_item * world + rank;
+    // round t hands item t * world + (rank + t) % world to this rank: a rotation, so that a rank
+    // does not keep the same (direction, half-column) of every distance (with 8 spans per distance
+    // and 8 ranks, plain i % world gave the x-major directions, whose REDs are strided, to four
+    // ranks and the cheaper y-major ones to the other four: 0.6 ms of barrier wait per step)
+    const unsigned long long item64 = (unsigned long long)s_item * world + (rank + s_item) % world;
     if (item64 >= n_items) break;
     const unsigned item = (unsigned)item64;
     const int ei = sweep_find_entry(item_prefix, n_entries, item);
@@ -983,11 +988,14 @@ __global__ void __launch_bounds__(kThreads) k_sweep_compact(
   }
 }
 
+// x-major batches (the 32 lanes share x and differ in y) accumulate into missT, a TRANSPOSED miss
+// plane (lin = y + x * ny): in the grid's own layout their REDs are nx * 4 bytes apart, one L2 line
+// per lane and step, while the y-major batches' are neighbours.  k_miss_fold adds missT back.
 __global__ void __launch_bounds__(kThreads) k_sweep_walk(
-  int32_t *__restrict__ miss, const SweepEntry *__restrict__ entries,
+  int32_t *__restrict__ miss, int32_t *__restrict__ missT, const SweepEntry *__restrict__ entries,
   unsigned *__restrict__ counters /* [1] batch count, [2] walk counter */,
   const int *__restrict__ batch_entry, const int *__restrict__ batch_mi,
-  const unsigned *__restrict__ batch_w, int sx, int sy, int nx, unsigned long long *__restrict__ stats)
+  const unsigned *__restrict__ batch_w, int sx, int sy, int nx, int ny, unsigned long long *__restrict__ stats)
 {
   const unsigned lane = threadIdx.x & 31;
   const unsigned nbatch = counters[1];
@@ -1018,7 +1026,8 @@ __global__ void __launch_bounds__(kThreads) k_sweep_walk(
     const int smajor = (E.dir == 0 || E.dir == 2) ? 1 : -1;
     int minor = xmajor ? sy : sx;
     const int major = xmajor ? sx : sy;
-    const int stride_major = xmajor ? 1 : nx, stride_minor = xmajor ? nx : 1;
+    int32_t *const plane = xmajor ? missT : miss;
+    const int stride_major = xmajor ? ny : nx, stride_minor = 1;
     int lin = major * stride_major + minor * stride_minor;
     const int dlin_major = smajor * stride_major, dlin_minor = sminor * stride_minor;
 #pragma unroll 1
@@ -1031,7 +1040,7 @@ __global__ void __launch_bounds__(kThreads) k_sweep_walk(
       const unsigned before = __shfl_sync(0xffffffffu, P, (start + 31) & 31);
       const unsigned sum = P - (start > 0 ? before : 0u);
       if (tail && sum) {
-        atomicAdd(miss + lin, (int32_t)sum);
+        atomicAdd(plane + lin, (int32_t)sum);
         ++st_physical;
       }
       num += add;
@@ -1046,6 +1055,37 @@ __global__ void __launch_bounds__(kThreads) k_sweep_walk(
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) st_physical += __shfl_xor_sync(0xffffffffu, st_physical, o);
   if (lane == 0 && st_physical) atomicAdd(stats + 2, st_physical);
+}
+
+// miss[x + y * nx] += missT[y + x * ny] over the cell rectangle [x0, x1] x [y0, y1] the x-major
+// lines can reach, and missT is zero again.  32 x 32 tiles through shared memory: both planes are
+// read and written in 128-byte rows.  Runs after k_sweep_walk on the same stream: plain adds.
+__global__ void __launch_bounds__(256) k_miss_fold(int32_t *__restrict__ miss, int32_t *__restrict__ missT, int nx,
+                                                   int ny, int x0, int y0, int x1, int y1)
+{
+  __shared__ int t[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int bx = x0 + (int)blockIdx.x * 32, by = y0 + (int)blockIdx.y * 32;
+  bool any = false;
+#pragma unroll
+  for (int j = ty; j < 32; j += 8) {
+    const int x = bx + j, y = by + tx;
+    int v = 0;
+    if (x <= x1 && y <= y1) {
+      const size_t o = (size_t)x * (unsigned)ny + (unsigned)y;
+      v = missT[o];
+      if (v) missT[o] = 0;
+    }
+    t[j][tx] = v;
+    any |= v != 0;
+  }
+  if (!__syncthreads_or(any)) return;
+#pragma unroll
+  for (int j = ty; j < 32; j += 8) {
+    const int x = bx + tx, y = by + j;
+    const int v = t[tx][j];
+    if (v) miss[(size_t)y * (unsigned)nx + (unsigned)x] += v;
+  }
 }
 
 // Stream-ordered barrier between the ranks of one node over peer memory: every rank owns a flag
