@@ -514,7 +514,7 @@ def main():
     if world > 1:
         sharding.init_context_comm(ctx, dev)
         merge = "NCCL all-reduce + reduce-scatter + all-gather"
-        if os.environ.get("GV_MERGE", "p2p") == "p2p" and sharding.enable_p2p(ctx, dev):
+        if os.environ.get("GV_MERGE", "nccl") == "p2p" and sharding.enable_p2p(ctx, dev):
             merge = "fused over NVLink peer memory (sweep sums peers' planes, finalise writes peers' grids)"
     multi = world > 1
 
@@ -645,7 +645,9 @@ def main():
             "config": workload_config(wl, F, world), "merge": merge,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "grid_crc": f"{crc:08x}", "grid_crc_steps": CRC_STEPS, "grid_crc_ranks_agree": ranks_agree,
-            "roofline": {"bound": "hbm", "kernel": "gv::k_points_tma (fused transform+project+label+bin, TMA-fed)",
+            "roofline": {"bound": "hbm", "kernel": "gv::k_points_pair (fused transform+project+label+bin, two points per "
+                                                   "thread on the packed f32x2 pipe) + k_box_masks + k_points_deferred[_list]: "
+                                                   "the whole gv_process_batch call",
                          "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None,
                          "algorithmic_bytes_per_launch": pts_bytes, "ms_per_launch": ms_points},
@@ -655,6 +657,10 @@ def main():
             "cells_per_s": {"logical": (st1["cells_logical"] - st0["cells_logical"]) / args.steps / (ms_step * 1e-3),
                             "physical": phys / (ms_step * 1e-3),
                             "distinct_ends_per_step": dst / args.steps},
+            "deferred_points": {"per_step": (st1["deferred_points"] - st0["deferred_points"]) / args.steps,
+                                "fraction": (st1["deferred_points"] - st0["deferred_points"]) / args.steps / max(1, n_local),
+                                "note": "points (rank 0) whose certified decisions were not provable and were redone by the "
+                                        "exact FP64 pass (k_points_deferred_list)"},
         }
         tr = measured_traffic()
         if tr:

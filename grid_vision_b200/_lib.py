@@ -44,7 +44,8 @@ class LShape(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("beams", C.c_uint64), ("cells_logical", C.c_uint64),
                 ("cells_physical", C.c_uint64), ("distinct_ends", C.c_uint64),
-                ("kernel_launches", C.c_uint64), ("merges", C.c_uint64), ("merge_ms_last", C.c_double)]
+                ("kernel_launches", C.c_uint64), ("merges", C.c_uint64), ("merge_ms_last", C.c_double),
+                ("deferred_points", C.c_uint64)]
 
 
 # every symbol include/gridvision_b200.h declares (checked by tests/test_abi.py)

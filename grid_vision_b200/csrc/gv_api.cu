@@ -35,7 +35,7 @@ enum {
   S_X, S_Y, S_Z, S_AOS, S_LAB, S_PIX, S_UV, S_BOX_RAW, S_BOX_F4, S_FRAME_OFF, S_BOX_OFF,
   S_TILE_PREFIX, S_TILE_START, S_TILE_END, S_TILE_BOX, S_CELL, S_FLAGS, S_FOOT_IN, S_FOOT_LAB,
   S_RECT, S_SMALL, S_OX, S_OY, S_OZ, S_SCAN0, S_SCAN1, S_SCAN2, S_SCAN3, S_UVZ, S_INDICES,
-  S_LABELS_IN, S_MASKS, S_SET_OFF, S_SWEEP, S_SWEEP_PREFIX, S_BATCH_ENTRY, S_BATCH_MI, S_BATCH_W, S_N2_TAB, S_N2_KEEP, S_N2_OUT, S_N2_OFF, S_N1_PLANES, S_N1_VALID, S_N1_SCORES, S_N1_STATE, S_DEFER, S_FRAMES, S_KNN_DEPTH, S_KNN_XYZ, S_COUNT
+  S_LABELS_IN, S_MASKS, S_SET_OFF, S_SWEEP, S_SWEEP_PREFIX, S_BATCH_ENTRY, S_BATCH_MI, S_BATCH_W, S_N2_TAB, S_N2_KEEP, S_N2_OUT, S_N2_OFF, S_N1_PLANES, S_N1_VALID, S_N1_SCORES, S_N1_STATE, S_DEFER, S_DEFER_LIST, S_DEFER_COUNT, S_FRAMES, S_KNN_DEPTH, S_KNN_XYZ, S_COUNT
 };
 
 constexpr size_t kPlanePad = 4096;  // slack cells so multi-GPU slabs can be equal-sized
@@ -102,7 +102,7 @@ struct gv_ctx {
   float Tb[16];
   BinDev bin{};
 
-  unsigned long long *d_stats = nullptr;  // beams, logical, physical, lines
+  unsigned long long *d_stats = nullptr;  // beams, logical, physical, lines, deferred points
   unsigned long long launches = 0;
   unsigned long long beams_bound = 0;  // host-side upper bound of beams since last finalize
 
@@ -867,7 +867,7 @@ int grid_init_impl(gv_ctx *ctx, double length_x, double length_y, double res, do
   GV_LAUNCH_CHECK();
   ctx->counts_dirty = ctx->ends_dirty = false;
   ctx->beams_bound = 0;
-  GV_CUDA(cudaMemsetAsync(ctx->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
+  GV_CUDA(cudaMemsetAsync(ctx->d_stats, 0, 8 * sizeof(unsigned long long), ctx->stream));
   return refresh_origin(ctx);
 }
 
@@ -922,9 +922,9 @@ int gv_create(gv_ctx **out, int device)
       cudaEventCreate(&ctx->ev_merge_t0) != cudaSuccess || cudaEventCreate(&ctx->ev_merge_t1) != cudaSuccess ||
       cudaMalloc(&ctx->d_flags, (kMaxPeers + 1) * sizeof(unsigned)) != cudaSuccess ||
       cudaMemset(ctx->d_flags, 0, (kMaxPeers + 1) * sizeof(unsigned)) != cudaSuccess ||
-      cudaMalloc(&ctx->d_stats, 4 * sizeof(unsigned long long)) != cudaSuccess ||
+      cudaMalloc(&ctx->d_stats, 8 * sizeof(unsigned long long)) != cudaSuccess ||
       cudaMalloc(&ctx->d_list_count, 4 * sizeof(unsigned)) != cudaSuccess ||
-      cudaMemset(ctx->d_stats, 0, 4 * sizeof(unsigned long long)) != cudaSuccess) {
+      cudaMemset(ctx->d_stats, 0, 8 * sizeof(unsigned long long)) != cudaSuccess) {
     cudaGetLastError();
     gv_destroy(ctx);
     return GV_ERR_CUDA;
@@ -1040,7 +1040,7 @@ int gv_get_stats(gv_ctx *ctx, gv_stats *out)
 {
   if (!ctx || !out) return GV_ERR_INVALID;
   GV_TRY(join_merge(ctx));
-  unsigned long long h[4];
+  unsigned long long h[5];
   GV_CUDA(cudaMemcpyAsync(h, ctx->d_stats, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
   GV_CUDA(cudaStreamSynchronize(ctx->stream));
   out->merges = ctx->merges;
@@ -1054,6 +1054,7 @@ int gv_get_stats(gv_ctx *ctx, gv_stats *out)
   out->cells_logical = h[1];
   out->cells_physical = h[2];
   out->distinct_ends = h[3];
+  out->deferred_points = h[4];
   out->kernel_launches = ctx->launches;
   return GV_OK;
 }
@@ -1534,7 +1535,7 @@ int gv_grid_reset(gv_ctx *ctx)
   GV_CUDA(cudaMemsetAsync(ctx->d_ends_buf[1], 0, padded * sizeof(unsigned long long), ctx->stream));
   k_fill_f32<<<ctx->num_sms * 4, kThreads, 0, ctx->stream>>>(ctx->d_occ, ctx->ncells, 0.5f);
   GV_LAUNCH_CHECK();
-  GV_CUDA(cudaMemsetAsync(ctx->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
+  GV_CUDA(cudaMemsetAsync(ctx->d_stats, 0, 8 * sizeof(unsigned long long), ctx->stream));
   ctx->counts_dirty = ctx->ends_dirty = false;
   ctx->beams_bound = 0;
   return GV_OK;
@@ -1817,12 +1818,12 @@ static void fill_fast_args(const PointArgs &a, unsigned *d_defer, FastArgs &f, b
   h.nires = -1.0 / g.res;
   h.Cx = b.c0xd / g.res + (double)bias_cells + magic;
   h.Cy = b.c0yd / g.res + (double)bias_cells + magic;
-  h.kb8 = ((unsigned)bias_cells << 16) + 8u;
+  h.kbm = ((unsigned)bias_cells << 16) + kIdxMargin;
   f.hi0 = 0x42380000u;
   f.klim_x = (unsigned)g.nx << 16;
   f.klim_y = (unsigned)g.ny << 16;
-  h.klim_x16 = f.klim_x - 16u;
-  h.klim_y16 = f.klim_y - 16u;
+  h.klim_xm = f.klim_x - 2u * kIdxMargin;
+  h.klim_ym = f.klim_y - 2u * kIdxMargin;
   h.nx = g.nx;
   f.ny = g.ny;
   // clip geometry: the same single-rounded float expressions as clip_end / oracle gvo_clip_end
@@ -1834,6 +1835,28 @@ static void fill_fast_args(const PointArgs &a, unsigned *d_defer, FastArgs &f, b
   f.paxf = f.nxf - b.oaxf; f.payf = f.nyf - b.oayf;
   f.cam = c;
   f.bin = b;
+}
+
+// The deferred stage of a certified launch: scan + compact the bitmap, then one thread per entry.
+// In a slots variable: a word index with a gw above 2^32 or an overflowing list is handled in place.
+static int launch_deferred(gv_ctx *ctx, const FastArgs &f, unsigned long long nwords)
+{
+  if (nwords == 0) return GV_OK;
+  unsigned nb = (unsigned)((nwords + kThreads - 1) / kThreads);
+  const unsigned capb = (unsigned)ctx->num_sms * 16u;
+  if (nb > capb) nb = capb;
+  DeferList dl;
+  // per scan CTA: room for 1/4 of its words to be non-zero (the certified paths defer < 1 % of the
+  // points); what does not fit is processed in place
+  const unsigned long long per_cta = (nwords + nb - 1) / nb;
+  dl.capacity = (unsigned)(per_cta / 4 + 64);
+  GV_TRY(reserve_t(ctx, S_DEFER_LIST, (size_t)nb * dl.capacity, &dl.items));
+  GV_TRY(reserve_t(ctx, S_DEFER_COUNT, (size_t)nb, &dl.count));
+  k_points_deferred<<<nb, kThreads, 0, ctx->stream>>>(f, dl);
+  GV_LAUNCH_CHECK();
+  k_points_deferred_list<<<nb, kThreads, 0, ctx->stream>>>(f, dl, ctx->d_stats + 4);
+  GV_LAUNCH_CHECK();
+  return GV_OK;
 }
 
 // tma: k_points_tma (persistent, bulk-copy fed) instead of k_points_fast
@@ -1908,13 +1931,7 @@ static int launch_points_fast(gv_ctx *ctx, FastArgs &f, bool bounded, bool tma, 
   }
   GV_LAUNCH_CHECK();
   // the points whose decisions could not be certified (a bitmap, normally < 0.1 % of the points)
-  const unsigned long long nwords = (unsigned long long)ntiles * (unsigned)(f.tile_pts >> 5);
-  unsigned nb = (unsigned)((nwords + kThreads - 1) / kThreads);
-  const unsigned cap = (unsigned)ctx->num_sms * 16u;
-  if (nb > cap) nb = cap;
-  k_points_deferred<<<nb, kThreads, 0, ctx->stream>>>(f);
-  GV_LAUNCH_CHECK();
-  return GV_OK;
+  return launch_deferred(ctx, f, (unsigned long long)ntiles * (unsigned)(f.tile_pts >> 5));
 }
 
 // Thresholds of k_points_pair's certified image test and the constants of its tile lookup, from
@@ -1937,7 +1954,7 @@ static void fill_pair_args(const FastArgs &f, PairArgs &p)
   p.oxf = h.oxf; p.oyf = h.oyf; p.noxf = -h.oxf; p.noyf = -h.oyf;
   p.rmax2f = h.rmax2f; p.rmaxf = w.rmaxf;
   p.nires = h.nires; p.Cx = h.Cx; p.Cy = h.Cy;
-  p.kb8 = h.kb8; p.nx = h.nx; p.klim_x16 = h.klim_x16; p.klim_y16 = h.klim_y16;
+  p.kbm = h.kbm; p.nx = h.nx; p.klim_xm = h.klim_xm; p.klim_ym = h.klim_ym;
   p.lab_min = h.lab_min;
   p.defer_stride = f.defer_stride;
   const double e6 = w.e6, slack = 1.0 + 4.76837158203125e-07;  // 1 + 2^-21
@@ -2026,13 +2043,7 @@ static int launch_points_col(gv_ctx *ctx, FastArgs &f, bool bounded, int frame0,
 #undef GV_COL_BL
 #undef GV_COL_LAUNCH
   GV_LAUNCH_CHECK();
-  const unsigned long long nwords = (unsigned long long)nframes * f.defer_stride;
-  unsigned nb = (unsigned)((nwords + kThreads - 1) / kThreads);
-  const unsigned cap = (unsigned)ctx->num_sms * 16u;
-  if (nb > cap) nb = cap;
-  k_points_deferred<<<nb, kThreads, 0, ctx->stream>>>(f);
-  GV_LAUNCH_CHECK();
-  return GV_OK;
+  return launch_deferred(ctx, f, (unsigned long long)nframes * f.defer_stride);
 }
 
 // ---- batch: the whole hot path, one kernel pass over the points ------------------------

@@ -587,6 +587,11 @@ __global__ void __launch_bounds__(kThreads) k_box_masks(const float4 *__restrict
   const int set = blockIdx.x;
   const int b0 = set_offsets[set], b1 = set_offsets[set + 1];
   const float S = (float)(1 << shift), D = rev32 ? 1.0f : 0.0f;
+  // the usual set (<= 256 boxes) is staged in shared memory once: every tile tests every box
+  __shared__ float4 s_b[kThreads];
+  const bool staged = b1 - b0 <= kThreads;
+  if (staged && b0 + (int)threadIdx.x < b1) s_b[threadIdx.x] = boxes[b0 + threadIdx.x];
+  __syncthreads();
   for (int t = threadIdx.x; t < tiles_x * tiles_y * words; t += kThreads) {
     const int w = t % words, tile = t / words;
     const float x0 = (float)(tile % tiles_x) * S, y0 = (float)(tile / tiles_x) * S;
@@ -594,7 +599,7 @@ __global__ void __launch_bounds__(kThreads) k_box_masks(const float4 *__restrict
     const int bw0 = b0 + w * 64;
     const int bw1 = bw0 + 64 < b1 ? bw0 + 64 : b1;
     for (int b = bw0; b < bw1; ++b) {
-      const float4 B = boxes[b];
+      const float4 B = staged ? s_b[b - b0] : boxes[b];
       const int bit = rev32 ? ((b - bw0) & 32) + 31 - ((b - bw0) & 31) : b - bw0;
       // rev32 (the certified kernels): the tile is widened by D = 1 px, because k_points_pair takes
       // the tile from its approximate pixel (within 1e-3 px of the reference's) without a straddle test

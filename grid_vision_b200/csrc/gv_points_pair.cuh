@@ -117,9 +117,9 @@ struct __align__(16) PairArgs {
   float oxf, oyf, one, pad0;                  // one = 1.0f, opaque to ptxas (see mad2)
   double nires, Cx;                           // index FMA (fast_point)
   double Cy;
-  unsigned kb8;
+  unsigned kbm;
   int nx;
-  unsigned klim_x16, klim_y16;
+  unsigned klim_xm, klim_ym;
   int lab_min;
   unsigned defer_stride;
 };
@@ -173,10 +173,10 @@ __device__ __forceinline__ void label_pair(const Boxes &bsrc, unsigned long long
 __device__ __forceinline__ void offmap_lane(const FastArgs &a, float bx, float by, unsigned tx, unsigned ty,
                                             bool word_ok, int &lin, unsigned &def, unsigned bit)
 {
-  const int sx = (int)tx, sy = (int)ty;  // k - 8, signed view
+  const int sx = (int)tx, sy = (int)ty;  // k - margin, signed view
   const bool out = !word_ok | (sx < -16) | (sy < -16) | (sx >= (int)a.klim_x) | (sy >= (int)a.klim_y);
   if (!out) {
-    def |= bit;  // within 2^-13 cells of a cell or map boundary
+    def |= bit;  // within a few 2^-16 cells of a cell or map boundary
   } else {
     // off-map endpoint: clip the free-space-only beam to the map (oracle gvo_clip_end, all float)
     const float eax = __fmul_rn(__fsub_rn(a.c0xf, bx), a.inv_resf);
@@ -295,15 +295,15 @@ __device__ __forceinline__ void pair_body(const FastArgs &a, const PairArgs &pa,
     const float bx0 = lo2(bx), bx1 = hi2(bx), by0 = lo2(by), by1 = hi2(by);
     const double rx0 = fma((double)bx0, pa.nires, pa.Cx), ry0 = fma((double)by0, pa.nires, pa.Cy);
     const double rx1 = fma((double)bx1, pa.nires, pa.Cx), ry1 = fma((double)by1, pa.nires, pa.Cy);
-    const unsigned tx0 = (unsigned)__double2loint(rx0) - pa.kb8, ty0 = (unsigned)__double2loint(ry0) - pa.kb8;
-    const unsigned tx1 = (unsigned)__double2loint(rx1) - pa.kb8, ty1 = (unsigned)__double2loint(ry1) - pa.kb8;
+    const unsigned tx0 = (unsigned)__double2loint(rx0) - pa.kbm, ty0 = (unsigned)__double2loint(ry0) - pa.kbm;
+    const unsigned tx1 = (unsigned)__double2loint(rx1) - pa.kbm, ty1 = (unsigned)__double2loint(ry1) - pa.kbm;
     bool wok0 = true, wok1 = true;
     if (!BOUNDED) {
       wok0 = ((unsigned)__double2hiint(rx0) == a.hi0) & ((unsigned)__double2hiint(ry0) == a.hi0);
       wok1 = ((unsigned)__double2hiint(rx1) == a.hi0) & ((unsigned)__double2hiint(ry1) == a.hi0);
     }
-    ins0 = wok0 & (tx0 < pa.klim_x16) & (ty0 < pa.klim_y16) & (max(tx0 & 0xffffu, ty0 & 0xffffu) < 0xfff0u);
-    ins1 = wok1 & (tx1 < pa.klim_x16) & (ty1 < pa.klim_y16) & (max(tx1 & 0xffffu, ty1 & 0xffffu) < 0xfff0u);
+    ins0 = wok0 & (tx0 < pa.klim_xm) & (ty0 < pa.klim_ym) & (max(tx0 & 0xffffu, ty0 & 0xffffu) < kFracLim);
+    ins1 = wok1 & (tx1 < pa.klim_xm) & (ty1 < pa.klim_ym) & (max(tx1 & 0xffffu, ty1 & 0xffffu) < kFracLim);
     lin0 = (int)(tx0 >> 16) + (int)(ty0 >> 16) * pa.nx;
     lin1 = (int)(tx1 >> 16) + (int)(ty1 >> 16) * pa.nx;
     // a lane without a usable point must not drag the warp into the off-map code

@@ -100,6 +100,7 @@ typedef struct {
   uint64_t kernel_launches;   /* kernels launched by this context so far                  */
   uint64_t merges;            /* gv_grid_finalize / _multi calls so far                    */
   double merge_ms_last;       /* device time of the last one (raycast [+ exchange] + finalise) */
+  uint64_t deferred_points;   /* points the certified kernels handed to the exact FP64 pass (since reset) */
 } gv_stats;
 
 /* ------------------------------------------------------------------ lifecycle --- */

@@ -69,7 +69,7 @@ def test_reference_struct_layouts():
         [0, 8, 16, 24, 32, 36]
     assert POINT_DTYPE.itemsize == 32  # pcl::PointXYZI
     from grid_vision_b200._lib import AccumParams, GridDesc, Stats
-    assert C.sizeof(AccumParams) == 24 and C.sizeof(GridDesc) == 48 and C.sizeof(Stats) == 56
+    assert C.sizeof(AccumParams) == 24 and C.sizeof(GridDesc) == 48 and C.sizeof(Stats) == 64
 
 
 def test_synthetic_workloads_match_baseline_configs():
