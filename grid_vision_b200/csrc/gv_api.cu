@@ -35,7 +35,7 @@ enum {
   S_X, S_Y, S_Z, S_AOS, S_LAB, S_PIX, S_UV, S_BOX_RAW, S_BOX_F4, S_FRAME_OFF, S_BOX_OFF,
   S_TILE_PREFIX, S_TILE_START, S_TILE_END, S_TILE_BOX, S_CELL, S_FLAGS, S_FOOT_IN, S_FOOT_LAB,
   S_RECT, S_SMALL, S_OX, S_OY, S_OZ, S_SCAN0, S_SCAN1, S_SCAN2, S_SCAN3, S_UVZ, S_INDICES,
-  S_LABELS_IN, S_MASKS, S_SET_OFF, S_SWEEP, S_SWEEP_PREFIX, S_BATCH_ENTRY, S_BATCH_MI, S_BATCH_W, S_N2_TAB, S_N2_KEEP, S_N2_OUT, S_N2_OFF, S_N1_PLANES, S_N1_VALID, S_N1_SCORES, S_N1_STATE, S_DEFER, S_DEFER_LIST, S_DEFER_COUNT, S_FRAMES, S_KNN_DEPTH, S_KNN_XYZ, S_COUNT
+  S_LABELS_IN, S_MASKS, S_SET_OFF, S_SWEEP, S_SWEEP_PREFIX, S_SWEEP_ITEM, S_BATCH_ENTRY, S_BATCH_MI, S_BATCH_W, S_N2_TAB, S_N2_KEEP, S_N2_OUT, S_N2_OFF, S_N1_PLANES, S_N1_VALID, S_N1_SCORES, S_N1_STATE, S_DEFER, S_DEFER_LIST, S_DEFER_COUNT, S_FRAMES, S_KNN_DEPTH, S_KNN_XYZ, S_COUNT
 };
 
 constexpr size_t kPlanePad = 4096;  // slack cells so multi-GPU slabs can be equal-sized
@@ -82,6 +82,7 @@ struct gv_ctx {
   unsigned *d_list_count = nullptr;  // work-item counter of the raycast sweep
   SweepEntry *d_sweep = nullptr;     // sweep table for the current start cell
   unsigned *d_sweep_prefix = nullptr;  // [n_sweep+1] first work item of each entry
+  int *d_sweep_item = nullptr;         // [n_sweep_items] entry of each work item
   int n_sweep = 0;
   unsigned n_sweep_items = 0;
   bool counts_dirty = false, ends_dirty = false;
@@ -566,14 +567,17 @@ int raycast_flush_impl(gv_ctx *ctx, unsigned rank, unsigned world, bool p2p_gath
   GV_TRY(reserve_t(ctx, S_BATCH_MI, max_batches * 32, &d_bmi));
   GV_TRY(reserve_t(ctx, S_BATCH_W, max_batches * 32, &d_bw));
   stage_mark(ctx, 2);
+  // one CTA per span this rank owns
+  unsigned nbc = (unsigned)(((unsigned long long)ctx->n_sweep_items + world - 1) / world);
+  if (nbc < 1u) nbc = 1u;
   if (p2p_gather)  // sums (and clears) the cells it owns in every rank's plane over NVLink
-    k_sweep_compact<true><<<nb, kThreads, 0, ctx->stream>>>(
-      ctx->d_ends, ctx->d_hit, ctx->d_miss, ctx->d_sweep, ctx->d_sweep_prefix, ctx->n_sweep, ctx->n_sweep_items,
+    k_sweep_compact<true><<<nbc, kThreads, 0, ctx->stream>>>(
+      ctx->d_ends, ctx->d_hit, ctx->d_miss, ctx->d_sweep, ctx->d_sweep_prefix, ctx->d_sweep_item, ctx->n_sweep, ctx->n_sweep_items,
       ctx->bin.sx, ctx->bin.sy, ctx->g.nx, rank, world, 1, ctx->d_list_count, d_bentry, d_bmi, d_bw, ctx->d_stats,
       ctx->peer_ends_buf[ctx->ends_cur]);
   else
-    k_sweep_compact<false><<<nb, kThreads, 0, ctx->stream>>>(
-      ctx->d_ends, ctx->d_hit, ctx->d_miss, ctx->d_sweep, ctx->d_sweep_prefix, ctx->n_sweep, ctx->n_sweep_items,
+    k_sweep_compact<false><<<nbc, kThreads, 0, ctx->stream>>>(
+      ctx->d_ends, ctx->d_hit, ctx->d_miss, ctx->d_sweep, ctx->d_sweep_prefix, ctx->d_sweep_item, ctx->n_sweep, ctx->n_sweep_items,
       ctx->bin.sx, ctx->bin.sy, ctx->g.nx, rank, world, world == 1 ? 1 : 0, ctx->d_list_count, d_bentry, d_bmi,
       d_bw, ctx->d_stats, ctx->peer_ends);
   GV_LAUNCH_CHECK();
@@ -657,6 +661,14 @@ int build_sweep_table(gv_ctx *ctx)
   GV_CUDA(cudaMemcpyAsync(ctx->d_sweep, ent.data(), ent.size() * sizeof(SweepEntry),
                           cudaMemcpyHostToDevice, ctx->stream));
   GV_CUDA(cudaMemcpyAsync(ctx->d_sweep_prefix, prefix.data(), prefix.size() * sizeof(unsigned),
+                          cudaMemcpyHostToDevice, ctx->stream));
+  // item -> entry, so that a span's CTA finds its entry with one load
+  std::vector<int> item_entry((size_t)items + 1);
+  for (size_t i = 0; i < ent.size(); ++i)
+    for (unsigned k = prefix[i]; k < prefix[i + 1]; ++k) item_entry[k] = (int)i;
+  GV_TRY(reserve(ctx, S_SWEEP_ITEM, item_entry.size() * sizeof(int), &p));
+  ctx->d_sweep_item = static_cast<int *>(p);
+  GV_CUDA(cudaMemcpyAsync(ctx->d_sweep_item, item_entry.data(), item_entry.size() * sizeof(int),
                           cudaMemcpyHostToDevice, ctx->stream));
   GV_CUDA(cudaStreamSynchronize(ctx->stream));  // host vectors die here
   ctx->n_sweep = (int)ent.size();

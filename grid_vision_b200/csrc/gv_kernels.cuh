@@ -875,7 +875,8 @@ constexpr int kSpanCells = 32 * kSpanChunks;
 template <bool P2P>
 __global__ void __launch_bounds__(kThreads) k_sweep_compact(
   unsigned long long *__restrict__ ends, int32_t *__restrict__ hit, int32_t *__restrict__ miss,
-  const SweepEntry *__restrict__ entries, const unsigned *__restrict__ item_prefix, int n_entries,
+  const SweepEntry *__restrict__ entries, const unsigned *__restrict__ item_prefix,
+  const int *__restrict__ item_entry, int n_entries,
   unsigned n_items, int sx, int sy, int nx, unsigned rank, unsigned world, int clear_ends,
   unsigned *__restrict__ counters /* [0] item counter, [1] batch count */,
   int *__restrict__ batch_entry, int *__restrict__ batch_mi, unsigned *__restrict__ batch_w,
@@ -884,14 +885,14 @@ __global__ void __launch_bounds__(kThreads) k_sweep_compact(
   constexpr int kWarps = kThreads / 32;
   constexpr int kPer = kSpanChunks / kWarps;  // chunks per warp
   static_assert(kSpanChunks % kWarps == 0, "span must split evenly over the warps");
-  __shared__ unsigned s_item, s_base;
+  __shared__ unsigned s_base;
   __shared__ int s_cnt[kSpanChunks], s_last[kWarps];
   const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   unsigned long long st_beams = 0, st_logical = 0, st_lines = 0;
-  for (;;) {
-    __syncthreads();  // s_item / s_cnt of the previous span are no longer read
-    if (threadIdx.x == 0) s_item = atomicAdd(counters, 1u);
-    __syncthreads();
+  // one span per CTA (grid-stride if the grid is smaller): CTAs are dispatched in index order, so
+  // the batch list still fills longest lines first
+  for (unsigned s_item = blockIdx.x;; s_item += gridDim.x) {
+    __syncthreads();  // s_cnt / s_base of the previous span are no longer read
     // round t hands item t * world + (rank + t) % world to this rank: a rotation, so that a rank
     // does not keep the same (direction, half-column) of every distance (with 8 spans per distance
     // and 8 ranks, plain i % world gave the x-major directions, whose REDs are strided, to four
@@ -899,7 +900,7 @@ __global__ void __launch_bounds__(kThreads) k_sweep_compact(
     const unsigned long long item64 = (unsigned long long)s_item * world + (rank + s_item) % world;
     if (item64 >= n_items) break;
     const unsigned item = (unsigned)item64;
-    const int ei = sweep_find_entry(item_prefix, n_entries, item);
+    const int ei = item_entry[item];  // (a binary search of item_prefix here cost ~13 dependent loads per CTA)
     const SweepEntry E = entries[ei];
     const int span0 = E.m0 + (int)(item - item_prefix[ei]) * kSpanCells;
     // four independent loads per thread
@@ -1027,35 +1028,35 @@ __global__ void __launch_bounds__(kThreads) k_sweep_walk(
     int num = den / 2;
     const int dminor = mi - (xmajor ? sy : sx);
     const int add = dminor >= 0 ? dminor : -dminor;
-    const int sminor = dminor >= 0 ? 1 : -1;
     const int smajor = (E.dir == 0 || E.dir == 2) ? 1 : -1;
-    int minor = xmajor ? sy : sx;
-    const int major = xmajor ? sx : sy;
     int32_t *const plane = xmajor ? missT : miss;
-    const int stride_major = xmajor ? ny : nx, stride_minor = 1;
-    int lin = major * stride_major + minor * stride_minor;
-    const int dlin_major = smajor * stride_major, dlin_minor = sminor * stride_minor;
+    // both planes put the minor coordinate in the fast index: cell = major * stride + minor
+    const int stride_major = xmajor ? ny : nx;
+    int lin = (xmajor ? sx : sy) * stride_major + (xmajor ? sy : sx);
+    const int dlin_major = smajor * stride_major, dlin_minor = dminor >= 0 ? 1 : -1;
+    const unsigned mask_le = 0xffffffffu >> (31u - lane);
+    const unsigned Pex = P - w;  // exclusive prefix
+    unsigned st_phys32 = 0u;
 #pragma unroll 1
     for (int k = 0; k < den; ++k) {
-      // runs of equal cells = runs of equal minor coordinate (monotone in the lane index)
-      const int prev = __shfl_up_sync(0xffffffffu, minor, 1);
-      const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || minor != prev);
-      const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
-      const int start = 31 - __clz((int)(heads & (0xffffffffu >> (31 - lane))));
-      const unsigned before = __shfl_sync(0xffffffffu, P, (start + 31) & 31);
-      const unsigned sum = P - (start > 0 ? before : 0u);
+      // every lane is at the same major coordinate and the minor coordinates are monotone in the
+      // lane index, so equal cells form contiguous lane runs: one RED per run (by its last lane),
+      // the run's weight a difference of the warp prefix sums
+      const int prev = __shfl_up_sync(0xffffffffu, lin, 1);
+      const unsigned heads = __ballot_sync(0xffffffffu, (lane == 0u) | (lin != prev));
+      const int start = 31 - __clz((int)(heads & mask_le));
+      const unsigned sum = P - __shfl_sync(0xffffffffu, Pex, start);
+      const bool tail = (((heads >> 1) | 0x80000000u) >> lane) & 1u;
       if (tail && sum) {
         atomicAdd(plane + lin, (int32_t)sum);
-        ++st_physical;
+        ++st_phys32;
       }
       num += add;
-      if (num >= den) {
-        num -= den;
-        minor += sminor;
-        lin += dlin_minor;
-      }
-      lin += dlin_major;
+      const bool carry = num >= den;
+      num -= carry ? den : 0;
+      lin += dlin_major + (carry ? dlin_minor : 0);
     }
+    st_physical += st_phys32;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) st_physical += __shfl_xor_sync(0xffffffffu, st_physical, o);
