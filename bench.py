@@ -292,11 +292,13 @@ def run_reference_arm(args, wl):
 
 def measured_traffic():
     """DRAM bytes per point of the fused kernel from the committed ncu capture (profiles/)."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            return json.load(f)
-    except Exception:
-        return None
+    for tag in ("r02", "r01"):
+        try:
+            with open(os.path.join(ROOT, "profiles", f"{tag}_traffic.json")) as f:
+                return json.load(f)
+        except Exception:
+            continue
+    return None
 
 
 def time_loop(torch, fn, iters, warm=3):

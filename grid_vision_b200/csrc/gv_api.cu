@@ -89,6 +89,7 @@ struct gv_ctx {
   bool multi_checked = false;  // ranks verified to share geometry + pose (gv_grid_finalize_multi)
   bool use_fast = true;  // $GV_NO_FAST=1 forces the generic k_points (A/B measurements)
   int fast_unroll = 2;   // $GV_FAST_U: points per thread per iteration of k_points_fast
+  int pair_waves = 32;           // $GV_PAIR_WAVES: CTA waves k_points_pair's grid aims at (fewer = longer run-length merging)
   int pair_minb = GV_PAIR_MINB;  // $GV_PAIR_MINB: CTAs per SM k_points_pair's register allocation aims at (3..6)
   bool col_hoist = false; // $GV_COL_HOIST=1: k_points_col keeps FastHot in registers (fewer instructions, 3 CTAs/SM)
   int fast_kind = 0;     // $GV_FAST_KIND: 0 k_points_pair where the layout allows it, else k_points_col (default),
@@ -963,6 +964,8 @@ int gv_create(gv_ctx **out, int device)
   if (const char *u = std::getenv("GV_COL_HOIST")) ctx->col_hoist = std::atoi(u) != 0;
   if (const char *u = std::getenv("GV_PAIR_MINB")) ctx->pair_minb = std::atoi(u);
   if (ctx->pair_minb < 3 || ctx->pair_minb > 6) ctx->pair_minb = GV_PAIR_MINB;
+  if (const char *u = std::getenv("GV_PAIR_WAVES")) ctx->pair_waves = std::atoi(u);
+  if (ctx->pair_waves < 1 || ctx->pair_waves > 64) ctx->pair_waves = 32;
   if (ctx->fast_kind != 1) ctx->use_tma = false;
   if (const char *u = std::getenv("GV_TMA_HOIST")) ctx->tma_hoist = std::atoi(u) != 0;
   if (const char *u = std::getenv("GV_L2_PERSIST")) ctx->l2_persist = std::atoi(u) != 0;
@@ -2000,7 +2003,7 @@ static int launch_points_col(gv_ctx *ctx, FastArgs &f, bool bounded, int frame0,
   const unsigned cols = ((max_pts + per_thread - 1) / per_thread + kThreads - 1) / kThreads;
   // enough CTAs for ~16 waves of 5 CTAs per SM, as few frame groups as that allows: the longer a
   // thread stays on its beam index, the more of the beam's repeats it merges before the RED
-  const unsigned want = (unsigned)ctx->num_sms * (f.pair ? (unsigned)ctx->pair_minb * 12u : 5u * 16u);
+  const unsigned want = (unsigned)ctx->num_sms * (f.pair ? (unsigned)(ctx->pair_minb * ctx->pair_waves) : 5u * 16u);
   unsigned groups = (want + cols - 1) / cols;
   if (groups > (unsigned)nframes) groups = (unsigned)nframes;
   if (groups < 1u) groups = 1u;

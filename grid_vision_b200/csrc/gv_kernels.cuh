@@ -873,7 +873,7 @@ constexpr int kSpanCells = 32 * kSpanChunks;
 // partitions the cells, so this CTA is the only reader of these cells on any rank.  This is the
 // all-reduce of the end-cell planes, restricted to what this rank walks, fused into the sweep.
 template <bool P2P>
-__global__ void __launch_bounds__(kThreads) k_sweep_compact(
+__global__ void __launch_bounds__(kThreads, 4) k_sweep_compact(
   unsigned long long *__restrict__ ends, int32_t *__restrict__ hit, int32_t *__restrict__ miss,
   const SweepEntry *__restrict__ entries, const unsigned *__restrict__ item_prefix,
   const int *__restrict__ item_entry, int n_entries,

@@ -278,10 +278,12 @@ __device__ __forceinline__ void pair_body(const FastArgs &a, const PairArgs &pa,
     const f32x2 r2 = fma2(mul2(dx, dx), one, mul2(dy, dy));
     ok0 = lo2(r2) < 1.0e30f;
     ok1 = hi2(r2) < 1.0e30f;
-    def |= (lo2(r2) >= 1.0e30f ? 1u : 0u) | (hi2(r2) >= 1.0e30f ? 2u : 0u);
     cap0 = lo2(r2) > pa.rmax2f;
     cap1 = hi2(r2) > pa.rmax2f;
+    // r2 >= 1e30 defers.  With a range cap (BOUNDED) such a lane is also capped: tested in there.
+    if (!BOUNDED) def |= (lo2(r2) >= 1.0e30f ? 1u : 0u) | (hi2(r2) >= 1.0e30f ? 2u : 0u);
     if (cap0 | cap1) {  // beyond the mapping range: free-space-only beam shortened to r_max
+      if (BOUNDED) def |= (lo2(r2) >= 1.0e30f ? 1u : 0u) | (hi2(r2) >= 1.0e30f ? 2u : 0u);
       const f32x2 sf = div_rn_inrange2(bc2(pa.rmaxf), sqrt_rn_inrange2(r2));
       const f32x2 cx = mad2(sf, dx, bc2(pa.oxf), one), cy = mad2(sf, dy, bc2(pa.oyf), one);
       bx = pk2(cap0 ? lo2(cx) : lo2(bx), cap1 ? hi2(cx) : hi2(bx));

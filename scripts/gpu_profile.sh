@@ -12,7 +12,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base fun
 echo "ncu list exit $?"
 if [ "${FULL:-1}" = "1" ]; then
 python bench.py $BENCH_ARGS > gpurun_out/plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on --kernel-name-base function --kernel-name regex:'^k_(points|sweep_compact|sweep_walk|finalize)' -s 4 -c 4 \
+ncu --set full --clock-control none --import-source on --kernel-name-base function --kernel-name regex:'^k_(points_pair|points_deferred|sweep_compact|sweep_walk|miss_fold|finalize)' -s ${SKIP:-7} -c 7 \
     -o gpurun_out/prof -f python bench.py $BENCH_ARGS > gpurun_out/ncu_full.log 2>&1
 echo "ncu full exit $?"
 fi
