@@ -675,13 +675,19 @@ def main():
                 import microbench
                 mb = microbench.run(local, reps=128)
                 out["atomic_peaks_ops_per_s"] = mb
-                red_peak = mb["red32_spread_4Mcells"]
+                spread, contig = mb["red32_spread_4Mcells"], mb["red32_contig_4Mcells"]
+                ach = phys / (ms_final * 1e-3)
                 out["roofline_k3"] = {
-                    "bound": "l2-atomic", "kernel": "gv::k_sweep_walk (one RED.32 per distinct cell per step)",
-                    "achieved": phys / (ms_final * 1e-3), "peak": red_peak, "unit": "RED/s",
-                    "frac": phys / (ms_final * 1e-3) / red_peak,
-                    "peak_source": "gv_microbench_atomics: RED.32, 32 independent L2-resident cells per warp; "
-                                   "the denominator time is the whole raycast+finalise phase"}
+                    "bound": "instruction issue (ALU pipe), under the L2 atomic ceilings",
+                    "kernel": "gv::k_sweep_walk (one RED.32 per distinct cell per step; both line families put the "
+                              "minor coordinate in the fast index, so a warp's REDs are neighbours)",
+                    "achieved": ach, "unit": "RED/s",
+                    "peak": contig, "frac": ach / contig,
+                    "peak_spread": spread, "frac_of_spread": ach / spread,
+                    "peak_source": "gv_microbench_atomics RED.32 on an L2-resident 4M-cell plane: `peak` = 32 consecutive "
+                                   "cells per warp instruction, `peak_spread` = 32 independent cells (one L2 line each); the "
+                                   "walk's REDs lie between the two patterns; the denominator time is the whole "
+                                   "raycast+finalise phase"}
             except Exception as e:  # measurement aid only
                 out["roofline_k3"] = {"error": str(e)}
             out["parity_sample"] = parity_sample(torch, gv, synth, ctx, dev, wl)

@@ -625,8 +625,12 @@ int build_sweep_table(gv_ctx *ctx)
   const int maxD = (nx > ny ? nx : ny);
   std::vector<SweepEntry> ent;
   ent.reserve(4 * (size_t)maxD + 1);
-  for (int D = maxD; D >= 1; --D) {
-    for (int dir = 0; dir < 4; ++dir) {
+  // Direction-major, longest distance first within a direction: the batches in flight at any time
+  // then stay inside one quadrant of the reachable disc, whose part of the miss plane fits L2 even
+  // for the 8192^2 map (interleaving the four directions made every RED of that map a DRAM
+  // read-modify-write), and the tail of the schedule is still made of short lines.
+  for (int dir = 0; dir < 4; ++dir) {
+    for (int D = maxD; D >= 1; --D) {
       SweepEntry e;
       e.dir = dir;
       e.D = D;

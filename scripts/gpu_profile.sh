@@ -15,5 +15,8 @@ python bench.py $BENCH_ARGS > gpurun_out/plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on --kernel-name-base function --kernel-name regex:'^k_(points_pair|points_deferred|sweep_compact|sweep_walk|miss_fold|finalize)' -s ${SKIP:-7} -c 7 \
     -o gpurun_out/prof -f python bench.py $BENCH_ARGS > gpurun_out/ncu_full.log 2>&1
 echo "ncu full exit $?"
+ncu -i gpurun_out/prof.ncu-rep --page raw --csv > gpurun_out/prof_raw.csv 2>/dev/null
+ncu -i gpurun_out/prof.ncu-rep --page source --csv --print-source sass --kernel-name-base function --kernel-name regex:'^k_points_pair' > gpurun_out/src_pair.csv 2>/dev/null
+ncu -i gpurun_out/prof.ncu-rep --page raw --csv --kernel-name-base function --kernel-name regex:'^k_points_pair' > gpurun_out/prof_pair_raw.csv 2>/dev/null
 fi
 ls -la gpurun_out/

@@ -35,8 +35,18 @@ for (txt, cur), (n, s) in zip(seq, inst):
     by[cur] += n
     sm[cur] += s
 tot = sum(by.values())
-src = open('/root/repo/grid_vision_b200/csrc/gv_kernels.cuh').read().split('\n')
+import os
+_root = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'grid_vision_b200', 'csrc')
+_src = {}
+def src_line(k):
+    if not k:
+        return ''
+    f = os.path.join(_root, k[0])
+    if k[0] not in _src:
+        _src[k[0]] = open(f).read().split('\n') if os.path.exists(f) else []
+    t = _src[k[0]]
+    return t[k[1] - 1].strip()[:88] if 0 < k[1] <= len(t) else ''
 print(f'total warp-inst {tot}, thread-inst/pt {tot * 32 / npts:.1f}, samples {sum(sm.values())}')
 for k, v in by.most_common(int(sys.argv[5]) if len(sys.argv) > 5 else 40):
-    t = src[k[1] - 1].strip()[:88] if k and k[0] == 'gv_kernels.cuh' else ''
+    t = src_line(k)
     print(f'{100 * v / tot:5.1f}% {v * 32 / npts:6.1f}/pt samp {100 * sm[k] / sum(sm.values()):4.1f}% {k[0][:14] if k else None}:{k[1] if k else 0} {t}')
