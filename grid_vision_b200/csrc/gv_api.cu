@@ -625,12 +625,11 @@ int build_sweep_table(gv_ctx *ctx)
   const int maxD = (nx > ny ? nx : ny);
   std::vector<SweepEntry> ent;
   ent.reserve(4 * (size_t)maxD + 1);
-  // Direction-major, longest distance first within a direction: the batches in flight at any time
-  // then stay inside one quadrant of the reachable disc, whose part of the miss plane fits L2 even
-  // for the 8192^2 map (interleaving the four directions made every RED of that map a DRAM
-  // read-modify-write), and the tail of the schedule is still made of short lines.
-  for (int dir = 0; dir < 4; ++dir) {
-    for (int D = maxD; D >= 1; --D) {
+  // Longest distance first, the four directions interleaved.  (Direction-major order, meant to keep
+  // the batches in flight inside one quadrant of the plane, measured slower on every config: C3
+  // raycast 0.44 -> 0.49 ms, C5 1.44 -> 1.51 ms.)
+  for (int D = maxD; D >= 1; --D) {
+    for (int dir = 0; dir < 4; ++dir) {
       SweepEntry e;
       e.dir = dir;
       e.D = D;

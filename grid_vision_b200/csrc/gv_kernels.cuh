@@ -829,7 +829,7 @@ struct SweepEntry {
   int m0, m1;  // inclusive range of the minor coordinate (absolute index), clipped to the map
 };
 
-// Scheduling: the span list is direction-major, decreasing D within a direction; rank r owns one span of every round of `world`
+// Scheduling: the span list is sorted by decreasing D; rank r owns one span of every round of `world`
 // spans (rotating, see k_sweep_compact) and
 // warps pull work through an atomic counter, longest first.  (Measured: static round-robin is
 // 20 % slower — most spans carry no beams and the busy ones cluster — and cutting lines into
