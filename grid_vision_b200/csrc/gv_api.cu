@@ -83,12 +83,16 @@ struct gv_ctx {
   SweepEntry *d_sweep = nullptr;     // sweep table for the current start cell
   unsigned *d_sweep_prefix = nullptr;  // [n_sweep+1] first work item of each entry
   int *d_sweep_item = nullptr;         // [n_sweep_items] entry of each work item
+  std::vector<int> h_sweep_D;          // host copies: distance of each entry (non-increasing) ...
+  std::vector<unsigned> h_sweep_prefix;  // ... and its first work item
   int n_sweep = 0;
   unsigned n_sweep_items = 0;
   bool counts_dirty = false, ends_dirty = false;
   bool multi_checked = false;  // ranks verified to share geometry + pose (gv_grid_finalize_multi)
   bool use_fast = true;  // $GV_NO_FAST=1 forces the generic k_points (A/B measurements)
   int fast_unroll = 2;   // $GV_FAST_U: points per thread per iteration of k_points_fast
+  int span_chunks = 32;          // 32-cell chunks per sweep span (32 / 64 / 128), chosen by build_sweep_table
+  int span_chunks_env = 0;       // $GV_SPAN_CHUNKS overrides the choice
   int pair_waves = 32;           // $GV_PAIR_WAVES: CTA waves k_points_pair's grid aims at (fewer = longer run-length merging)
   int pair_minb = GV_PAIR_MINB;  // $GV_PAIR_MINB: CTAs per SM k_points_pair's register allocation aims at (3..6)
   bool col_hoist = false; // $GV_COL_HOIST=1: k_points_col keeps FastHot in registers (fewer instructions, 3 CTAs/SM)
@@ -568,19 +572,41 @@ int raycast_flush_impl(gv_ctx *ctx, unsigned rank, unsigned world, bool p2p_gath
   GV_TRY(reserve_t(ctx, S_BATCH_MI, max_batches * 32, &d_bmi));
   GV_TRY(reserve_t(ctx, S_BATCH_W, max_batches * 32, &d_bw));
   stage_mark(ctx, 2);
+  // Single GPU with a range cap: the table is sorted by decreasing distance, so the entries no
+  // beam of this sweep can reach are a prefix of it (multi-GPU: other ranks' caps are not known here)
+  unsigned item0 = 0u;
+  int reach = 2147483647 / 2;
+  if (world == 1 && ctx->sweep_reach < 1.0e9) {
+    reach = (int)ctx->sweep_reach;
+    size_t lo = 0, hi = ctx->h_sweep_D.size();  // first entry with D <= reach (D is non-increasing)
+    while (lo < hi) {
+      const size_t mid = (lo + hi) / 2;
+      if (ctx->h_sweep_D[mid] > reach) lo = mid + 1;
+      else hi = mid;
+    }
+    if (lo < ctx->h_sweep_prefix.size()) item0 = ctx->h_sweep_prefix[lo];
+  }
   // one CTA per span this rank owns
-  unsigned nbc = (unsigned)(((unsigned long long)ctx->n_sweep_items + world - 1) / world);
+  unsigned nbc = (unsigned)(((unsigned long long)(ctx->n_sweep_items - item0) + world - 1) / world);
   if (nbc < 1u) nbc = 1u;
-  if (p2p_gather)  // sums (and clears) the cells it owns in every rank's plane over NVLink
-    k_sweep_compact<true><<<nbc, kThreads, 0, ctx->stream>>>(
-      ctx->d_ends, ctx->d_hit, ctx->d_miss, ctx->d_sweep, ctx->d_sweep_prefix, ctx->d_sweep_item, ctx->n_sweep, ctx->n_sweep_items,
-      ctx->bin.sx, ctx->bin.sy, ctx->g.nx, rank, world, 1, ctx->d_list_count, d_bentry, d_bmi, d_bw, ctx->d_stats,
-      ctx->peer_ends_buf[ctx->ends_cur]);
-  else
-    k_sweep_compact<false><<<nbc, kThreads, 0, ctx->stream>>>(
-      ctx->d_ends, ctx->d_hit, ctx->d_miss, ctx->d_sweep, ctx->d_sweep_prefix, ctx->d_sweep_item, ctx->n_sweep, ctx->n_sweep_items,
-      ctx->bin.sx, ctx->bin.sy, ctx->g.nx, rank, world, world == 1 ? 1 : 0, ctx->d_list_count, d_bentry, d_bmi,
-      d_bw, ctx->d_stats, ctx->peer_ends);
+#define GV_COMPACT(PP, CC, CLEAR, PEERS)                                                                          \
+  k_sweep_compact<PP, CC><<<nbc, kThreads, 0, ctx->stream>>>(                                                       \
+    ctx->d_ends, ctx->d_hit, ctx->d_miss, ctx->d_sweep, ctx->d_sweep_prefix, ctx->d_sweep_item, ctx->n_sweep,       \
+    ctx->n_sweep_items, item0, reach, ctx->bin.sx, ctx->bin.sy, ctx->g.nx, rank, world, CLEAR, ctx->d_list_count, d_bentry, d_bmi, \
+    d_bw, ctx->d_stats, PEERS)
+  // p2p_gather: sums (and clears) the cells it owns in every rank's plane over NVLink
+  const int clear = p2p_gather ? 1 : (world == 1 ? 1 : 0);
+  if (ctx->span_chunks == 128) {
+    if (p2p_gather) GV_COMPACT(true, 128, clear, ctx->peer_ends_buf[ctx->ends_cur]);
+    else GV_COMPACT(false, 128, clear, ctx->peer_ends);
+  } else if (ctx->span_chunks == 64) {
+    if (p2p_gather) GV_COMPACT(true, 64, clear, ctx->peer_ends_buf[ctx->ends_cur]);
+    else GV_COMPACT(false, 64, clear, ctx->peer_ends);
+  } else {
+    if (p2p_gather) GV_COMPACT(true, 32, clear, ctx->peer_ends_buf[ctx->ends_cur]);
+    else GV_COMPACT(false, 32, clear, ctx->peer_ends);
+  }
+#undef GV_COMPACT
   GV_LAUNCH_CHECK();
   stage_mark(ctx, 3);
   k_sweep_walk<<<nb, kThreads, 0, ctx->stream>>>(ctx->d_miss, ctx->d_missT, ctx->d_sweep, ctx->d_list_count, d_bentry,
@@ -623,6 +649,10 @@ int build_sweep_table(gv_ctx *ctx)
   if (!ctx->bin.origin_ok) return GV_OK;
   const int nx = ctx->g.nx, ny = ctx->g.ny, sx = ctx->bin.sx, sy = ctx->bin.sy;
   const int maxD = (nx > ny ? nx : ny);
+  // span size: see k_sweep_compact
+  ctx->span_chunks = maxD > 2048 ? 128 : 32;
+  if (ctx->span_chunks_env == 32 || ctx->span_chunks_env == 64 || ctx->span_chunks_env == 128)
+    ctx->span_chunks = ctx->span_chunks_env;
   std::vector<SweepEntry> ent;
   ent.reserve(4 * (size_t)maxD + 1);
   // Longest distance first, the four directions interleaved.  (Direction-major order, meant to keep
@@ -653,7 +683,7 @@ int build_sweep_table(gv_ctx *ctx)
   unsigned long long items = 0;
   for (size_t i = 0; i < ent.size(); ++i) {
     prefix[i] = (unsigned)items;
-    items += (unsigned long long)(ent[i].m1 - ent[i].m0) / (unsigned long long)kSpanCells + 1ull;
+    items += (unsigned long long)(ent[i].m1 - ent[i].m0) / (unsigned long long)(32 * ctx->span_chunks) + 1ull;
   }
   GV_REQUIRE(items < 4294967295ull, GV_ERR_INVALID, "sweep table too large");
   prefix[ent.size()] = (unsigned)items;
@@ -677,6 +707,9 @@ int build_sweep_table(gv_ctx *ctx)
   GV_CUDA(cudaStreamSynchronize(ctx->stream));  // host vectors die here
   ctx->n_sweep = (int)ent.size();
   ctx->n_sweep_items = (unsigned)items;
+  ctx->h_sweep_D.resize(ent.size());
+  for (size_t i = 0; i < ent.size(); ++i) ctx->h_sweep_D[i] = ent[i].D;
+  ctx->h_sweep_prefix = prefix;
   return GV_OK;
 }
 
@@ -967,6 +1000,7 @@ int gv_create(gv_ctx **out, int device)
   if (const char *u = std::getenv("GV_COL_HOIST")) ctx->col_hoist = std::atoi(u) != 0;
   if (const char *u = std::getenv("GV_PAIR_MINB")) ctx->pair_minb = std::atoi(u);
   if (ctx->pair_minb < 3 || ctx->pair_minb > 6) ctx->pair_minb = GV_PAIR_MINB;
+  if (const char *u = std::getenv("GV_SPAN_CHUNKS")) ctx->span_chunks_env = std::atoi(u);
   if (const char *u = std::getenv("GV_PAIR_WAVES")) ctx->pair_waves = std::atoi(u);
   if (ctx->pair_waves < 1 || ctx->pair_waves > 64) ctx->pair_waves = 32;
   if (ctx->fast_kind != 1) ctx->use_tma = false;

@@ -862,8 +862,9 @@ __device__ __forceinline__ size_t sweep_end_cell(const SweepEntry &E, int mc, in
 // cells carrying beams this keeps ~3x more lanes busy than walking 32 raw cells at a time, and
 // a dense span (the map border, where every clipped beam ends) is spread over many warps
 // instead of being walked batch after batch by one.
-constexpr int kSpanChunks = 32;
-constexpr int kSpanCells = 32 * kSpanChunks;
+// CHUNKS (32-cell chunks per span, template parameter): 32 for maps up to 2048 cells a side; larger,
+// sparser maps use 128, so that a span's few end cells do not each drag a mostly-padded batch of 32
+// lanes through thousands of steps (BASELINE config 5: 5 lines per 1024-cell span).
 
 // One CTA per span: 8 warps x 4 chunks, four independent loads per thread, a block prefix over
 // the per-chunk ballots, one atomic per span to reserve its batches.  (A warp-per-span version
@@ -872,17 +873,18 @@ constexpr int kSpanCells = 32 * kSpanChunks;
 // NVLink loads and every rank's cell is cleared with NVLink stores, right here: span ownership
 // partitions the cells, so this CTA is the only reader of these cells on any rank.  This is the
 // all-reduce of the end-cell planes, restricted to what this rank walks, fused into the sweep.
-template <bool P2P>
-__global__ void __launch_bounds__(kThreads, 4) k_sweep_compact(
+template <bool P2P, int kSpanChunks>
+__global__ void __launch_bounds__(kThreads, kSpanChunks <= 32 ? 4 : 2) k_sweep_compact(
   unsigned long long *__restrict__ ends, int32_t *__restrict__ hit, int32_t *__restrict__ miss,
   const SweepEntry *__restrict__ entries, const unsigned *__restrict__ item_prefix,
   const int *__restrict__ item_entry, int n_entries,
-  unsigned n_items, int sx, int sy, int nx, unsigned rank, unsigned world, int clear_ends,
+  unsigned n_items, unsigned item0, int reach, int sx, int sy, int nx, unsigned rank, unsigned world, int clear_ends,
   unsigned *__restrict__ counters /* [0] item counter, [1] batch count */,
   int *__restrict__ batch_entry, int *__restrict__ batch_mi, unsigned *__restrict__ batch_w,
   unsigned long long *__restrict__ stats, const __grid_constant__ Peers<unsigned long long> peer_ends)
 {
   constexpr int kWarps = kThreads / 32;
+  constexpr int kSpanCells = 32 * kSpanChunks;
   constexpr int kPer = kSpanChunks / kWarps;  // chunks per warp
   static_assert(kSpanChunks % kWarps == 0, "span must split evenly over the warps");
   __shared__ unsigned s_base;
@@ -897,12 +899,20 @@ __global__ void __launch_bounds__(kThreads, 4) k_sweep_compact(
     // does not keep the same (direction, half-column) of every distance (with 8 spans per distance
     // and 8 ranks, plain i % world gave the x-major directions, whose REDs are strided, to four
     // ranks and the cheaper y-major ones to the other four: 0.6 ms of barrier wait per step)
-    const unsigned long long item64 = (unsigned long long)s_item * world + (rank + s_item) % world;
+    // item0 / reach (single GPU with a range cap): no beam binned since the last sweep ends farther than
+    // `reach` cells from the start cell on either axis, so the items of longer distances (the first
+    // item0 of the table) are not launched at all and a span wholly beyond reach on the minor axis
+    // returns before it reads anything (a 8192^2 map with 120 m rays: 2/3 of the end-cell plane)
+    const unsigned long long item64 = item0 + (unsigned long long)s_item * world + (rank + s_item) % world;
     if (item64 >= n_items) break;
     const unsigned item = (unsigned)item64;
     const int ei = item_entry[item];  // (a binary search of item_prefix here cost ~13 dependent loads per CTA)
     const SweepEntry E = entries[ei];
     const int span0 = E.m0 + (int)(item - item_prefix[ei]) * kSpanCells;
+    {
+      const int sm = E.dir < 2 ? sy : sx;  // the start cell's minor coordinate
+      if (E.dir < 4 && (span0 > sm + reach || span0 + kSpanCells - 1 < sm - reach)) continue;  // block-uniform
+    }
     // four independent loads per thread
     unsigned long long e[kPer];
     size_t elin[kPer];
