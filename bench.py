@@ -364,6 +364,45 @@ def timed_batch(torch, gv, synth, ctx, dev, wl, frames, iters, adversarial=False
             "distinct_end_cells": per("distinct_ends"), "grid_cells": wl.cells}
 
 
+def timed_scan_graph(torch, gv, synth, dev, wl, iters):
+    """One scan -> fuse + bin + raycast + finalise, captured once as a CUDA graph (gv_graph_*) and
+    replayed: the node's 20 Hz call pattern with one launch per scan."""
+    P = wl.points_per_frame
+    stream = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(stream), gv.Context(dev.index or 0) as ctx:
+        ctx.set_cameras(wl.K().reshape(1, 9), [[wl.image_w, wl.image_h]], synth.camera_extrinsics(1))
+        ctx.grid_init_cells(wl.grid_nx, wl.grid_ny, wl.resolution)
+        ctx.set_base_transform(synth.T_base_lidar())
+        xyz = synth.make_scans(wl, frames=1, device=dev)
+        boxes = synth.make_boxes(wl, frame=0)
+        d_boxes = torch.from_numpy(boxes.view(np.uint8).copy()).to(dev)
+        lab = torch.empty(P, dtype=torch.int16, device=dev)
+        fo = np.array([0, P], np.uint64)
+        bo = np.array([0, len(boxes)], np.int32)
+        prm = gv.accum_params(r_max=wl.r_max)
+
+        def one():
+            ctx.process_batch(xyz[0], xyz[1], xyz[2], fo, d_boxes, bo, prm, lab)
+            ctx.grid_finalize(1)
+        one()
+        stream.synchronize()
+        ctx.graph_begin()
+        one()
+        gid = ctx.graph_end()
+        for _ in range(5):
+            ctx.graph_launch(gid)
+        stream.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(iters):
+            ctx.graph_launch(gid)
+        b.record(stream)
+        stream.synchronize()
+        ms = a.elapsed_time(b) / iters
+        ctx.graph_destroy(gid)
+    return {"workload": wl.name + " (one CUDA-graph launch per scan)", "ms": ms, "points_per_s": P / (ms * 1e-3)}
+
+
 def other_configs(torch, gv, synth, ctx, dev):
     """The remaining BASELINE.json configs and the hard-input variant of C3, resident inputs,
     CUDA-event timed (N = 1 only).  Parity for every one of them is in tests/."""
@@ -373,6 +412,10 @@ def other_configs(torch, gv, synth, ctx, dev):
         r = timed_batch(torch, gv, synth, ctx, dev, wl, 1, 50)
         out[f"C{wl.config_id}"] = {k: r[k] for k in ("workload", "ms", "ms_points_kernel", "ms_raycast_finalize",
                                                       "points_per_s")}
+        try:
+            out[f"C{wl.config_id}_graph"] = timed_scan_graph(torch, gv, synth, dev, wl, 200)
+        except Exception as e:  # measurement aid only
+            out[f"C{wl.config_id}_graph"] = {"error": str(e)}
     # C4: 6-camera rig, 300 boxes, 1M-point cloud (fusion only, one label plane per camera)
     wl = synth.C4
     xyz = synth.make_scans(wl, frames=1, device=dev)

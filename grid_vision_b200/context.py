@@ -86,6 +86,21 @@ class Context:
             self._check(self._lib.gv_set_stream(self._h, C.c_void_p(s)), "gv_set_stream")
             self._bound_stream = s
 
+    # ---- CUDA graphs: capture a sequence of device-pointer calls once, replay it with one launch
+    def graph_begin(self):
+        self._check(self._lib.gv_graph_begin(self._h), "gv_graph_begin")
+
+    def graph_end(self) -> int:
+        gid = C.c_int32(-1)
+        self._check(self._lib.gv_graph_end(self._h, C.byref(gid)), "gv_graph_end")
+        return int(gid.value)
+
+    def graph_launch(self, gid: int):
+        self._check(self._lib.gv_graph_launch(self._h, C.c_int32(gid)), "gv_graph_launch")
+
+    def graph_destroy(self, gid: int):
+        self._check(self._lib.gv_graph_destroy(self._h, C.c_int32(gid)), "gv_graph_destroy")
+
     def stats(self) -> dict:
         st = Stats()
         self._check(self._lib.gv_get_stats(self._h, C.byref(st)), "gv_get_stats")

@@ -91,6 +91,14 @@ struct gv_ctx {
   bool multi_checked = false;  // ranks verified to share geometry + pose (gv_grid_finalize_multi)
   bool use_fast = true;  // $GV_NO_FAST=1 forces the generic k_points (A/B measurements)
   int fast_unroll = 2;   // $GV_FAST_U: points per thread per iteration of k_points_fast
+  // CUDA graphs of captured call sequences (gv_graph_*)
+  struct GraphSlot {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    size_t nodes = 0;
+  };
+  std::vector<GraphSlot> graphs;
+  bool capturing = false;
   int span_chunks = 32;          // 32-cell chunks per sweep span (32 / 64 / 128), chosen by build_sweep_table
   int span_chunks_env = 0;       // $GV_SPAN_CHUNKS overrides the choice
   int pair_waves = 32;           // $GV_PAIR_WAVES: CTA waves k_points_pair's grid aims at (fewer = longer run-length merging)
@@ -212,6 +220,8 @@ int reserve(gv_ctx *ctx, int slot, size_t bytes, void **out)
   Scratch &s = ctx->s[slot];
   if (bytes == 0) bytes = 16;
   if (s.cap < bytes) {
+    GV_REQUIRE(!ctx->capturing, GV_ERR_STATE,
+               "a scratch buffer would have to grow during graph capture: run the call sequence once before gv_graph_begin");
     // growing a scratch slot may free memory a previous async kernel still reads
     GV_CUDA(cudaStreamSynchronize(ctx->stream));
     if (ctx->merge_stream && ctx->merge_stream != ctx->stream) GV_CUDA(cudaStreamSynchronize(ctx->merge_stream));
@@ -1034,6 +1044,11 @@ void gv_destroy(gv_ctx *ctx)
   }
   for (auto &e : ctx->tev)
     if (e) cudaEventDestroy(e);
+  for (auto &g : ctx->graphs)
+    if (g.exec) {
+      cudaGraphExecDestroy(g.exec);
+      cudaGraphDestroy(g.graph);
+    }
 #ifdef GV_WITH_NCCL
   if (ctx->comm) ncclCommDestroy(ctx->comm);
 #endif
@@ -1085,6 +1100,73 @@ int gv_set_stream(gv_ctx *ctx, void *stream)
   // the handle is used as given: NULL is the legacy default stream (torch's default current
   // stream), not "reset"; gv_stream() of a fresh context returns its private stream
   ctx->stream = (cudaStream_t)stream;
+  return GV_OK;
+}
+
+// ---- CUDA graphs: a captured sequence of device-pointer calls replayed with one launch ----
+int gv_graph_begin(gv_ctx *ctx)
+{
+  if (!ctx) return GV_ERR_INVALID;
+  GV_CUDA(cudaSetDevice(ctx->device));
+  GV_REQUIRE(!ctx->capturing, GV_ERR_STATE, "gv_graph_begin: a capture is already open");
+  GV_REQUIRE(ctx->world == 1, GV_ERR_STATE, "gv_graph_begin: single-GPU contexts only");
+  GV_REQUIRE(ctx->stream != nullptr && ctx->stream != cudaStreamLegacy && ctx->stream != cudaStreamPerThread,
+             GV_ERR_STATE, "gv_graph_begin: the context runs on the default stream, which cannot be captured "
+                           "(gv_set_stream with a created stream, or keep the context's own)");
+  GV_TRY(join_merge(ctx));
+  GV_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+  ctx->capturing = true;
+  return GV_OK;
+}
+
+int gv_graph_end(gv_ctx *ctx, int32_t *graph_id)
+{
+  if (!ctx || !graph_id) return GV_ERR_INVALID;
+  GV_CUDA(cudaSetDevice(ctx->device));
+  GV_REQUIRE(ctx->capturing, GV_ERR_STATE, "gv_graph_end without gv_graph_begin");
+  ctx->capturing = false;
+  gv_ctx::GraphSlot g;
+  const cudaError_t e = cudaStreamEndCapture(ctx->stream, &g.graph);
+  if (e != cudaSuccess || g.graph == nullptr) {
+    cudaGetLastError();
+    return ctx->fail(GV_ERR_CUDA, "graph capture failed (%s): a captured call synchronised, allocated or copied "
+                                   "from pageable memory; run the sequence once before capturing",
+                     cudaGetErrorString(e));
+  }
+  GV_CUDA(cudaGraphGetNodes(g.graph, nullptr, &g.nodes));
+  if (cudaGraphInstantiate(&g.exec, g.graph, 0) != cudaSuccess) {
+    cudaGraphDestroy(g.graph);
+    cudaGetLastError();
+    return ctx->fail(GV_ERR_CUDA, "cudaGraphInstantiate failed");
+  }
+  ctx->graphs.push_back(g);
+  *graph_id = (int32_t)ctx->graphs.size() - 1;
+  return GV_OK;
+}
+
+int gv_graph_launch(gv_ctx *ctx, int32_t graph_id)
+{
+  if (!ctx) return GV_ERR_INVALID;
+  GV_REQUIRE(graph_id >= 0 && (size_t)graph_id < ctx->graphs.size() && ctx->graphs[graph_id].exec, GV_ERR_INVALID,
+             "no such graph %d", graph_id);
+  GV_REQUIRE(!ctx->capturing, GV_ERR_STATE, "gv_graph_launch during a capture");
+  GV_CUDA(cudaGraphLaunch(ctx->graphs[graph_id].exec, ctx->stream));
+  ctx->launches += ctx->graphs[graph_id].nodes;
+  return GV_OK;
+}
+
+int gv_graph_destroy(gv_ctx *ctx, int32_t graph_id)
+{
+  if (!ctx) return GV_ERR_INVALID;
+  GV_REQUIRE(graph_id >= 0 && (size_t)graph_id < ctx->graphs.size(), GV_ERR_INVALID, "no such graph %d", graph_id);
+  gv_ctx::GraphSlot &g = ctx->graphs[graph_id];
+  if (g.exec) {
+    GV_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaGraphExecDestroy(g.exec);
+    cudaGraphDestroy(g.graph);
+    g.exec = nullptr;
+    g.graph = nullptr;
+  }
   return GV_OK;
 }
 
@@ -1786,7 +1868,7 @@ int gv_grid_finalize(gv_ctx *ctx, int32_t k_decay, const double *corners, int nf
 // cache (ncu, round 2: half of the RED sectors missed L2 without it).  on = false clears it.
 static void set_ends_window(gv_ctx *ctx, bool on)
 {
-  if (!ctx->persist_bytes || !ctx->max_window) return;
+  if (!ctx->persist_bytes || !ctx->max_window || ctx->capturing) return;
   cudaStreamAttrValue v;
   memset(&v, 0, sizeof(v));
   if (on) {

@@ -123,6 +123,19 @@ GV_API void *gv_stream(gv_ctx *ctx);               /* cudaStream_t */
 GV_API int gv_set_stream(gv_ctx *ctx, void *stream);
 GV_API int gv_get_stats(gv_ctx *ctx, gv_stats *out);
 
+/* CUDA graphs for the node's per-scan call pattern (ref: src/grid_vision_node.cpp:139-237 runs the
+ * same fusion + grid update for every scan at 20 Hz): the device-pointer calls made between
+ * gv_graph_begin and gv_graph_end (gv_process_batch_dev, gv_grid_accumulate_dev, gv_grid_finalize,
+ * gv_grid_update*, ...) are captured from the context stream instead of executed, and gv_graph_launch
+ * replays them with ONE launch.  The captured calls read and write the same device buffers at every
+ * replay (refill them in place), with the arguments they were captured with.  Run the sequence
+ * once, un-captured, first: a captured call may not allocate, synchronise or copy from pageable
+ * memory (GV_ERR_STATE / GV_ERR_CUDA otherwise).  Single-GPU contexts on a non-default stream. */
+GV_API int gv_graph_begin(gv_ctx *ctx);
+GV_API int gv_graph_end(gv_ctx *ctx, int32_t *graph_id);
+GV_API int gv_graph_launch(gv_ctx *ctx, int32_t graph_id);
+GV_API int gv_graph_destroy(gv_ctx *ctx, int32_t graph_id);
+
 /* ------------------------------------------------------------ fusion (R1-R5) --- */
 /* Camera rig.  K: ncam x 9 (ref: src/object_detection.cpp:241-247 setIntrinsicMatrix);
  * T_cam_lidar: ncam x 16, the float matrix pcl_ros::transformPointCloud applies
