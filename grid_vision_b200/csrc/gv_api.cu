@@ -99,6 +99,8 @@ struct gv_ctx {
   };
   std::vector<GraphSlot> graphs;
   bool capturing = false;
+  int walk_seg = 64;             // $GV_WALK_SEG: steps per piece when a small sweep's lines are cut (0: never)
+  long long walk_seg_max_beams = 4ll << 20;  // sweeps of more beams than this walk whole lines (throughput mode)
   int span_chunks = 32;          // 32-cell chunks per sweep span (32 / 64 / 128), chosen by build_sweep_table
   int span_chunks_env = 0;       // $GV_SPAN_CHUNKS overrides the choice
   int pair_waves = 32;           // $GV_PAIR_WAVES: CTA waves k_points_pair's grid aims at (fewer = longer run-length merging)
@@ -619,8 +621,17 @@ int raycast_flush_impl(gv_ctx *ctx, unsigned rank, unsigned world, bool p2p_gath
 #undef GV_COMPACT
   GV_LAUNCH_CHECK();
   stage_mark(ctx, 3);
+  // small sweeps (a scan or two): cut the lines into pieces so that no warp walks a whole long line alone
+  unsigned nseg = 1u;
+  const int seg = ctx->walk_seg;
+  if (world == 1 && seg > 0 && ctx->beams_bound <= (unsigned long long)ctx->walk_seg_max_beams) {
+    int maxD = ctx->h_sweep_D.empty() ? 0 : ctx->h_sweep_D[0];
+    if (reach < maxD) maxD = reach;
+    nseg = (unsigned)((maxD + seg - 1) / seg);
+    if (nseg < 1u) nseg = 1u;
+  }
   k_sweep_walk<<<nb, kThreads, 0, ctx->stream>>>(ctx->d_miss, ctx->d_missT, ctx->d_sweep, ctx->d_list_count, d_bentry,
-                                                 d_bmi, d_bw, ctx->bin.sx, ctx->bin.sy, ctx->g.nx, ctx->g.ny,
+                                                 d_bmi, d_bw, ctx->bin.sx, ctx->bin.sy, ctx->g.nx, ctx->g.ny, nseg, seg,
                                                  ctx->d_stats);
   GV_LAUNCH_CHECK();
   {
@@ -1011,6 +1022,8 @@ int gv_create(gv_ctx **out, int device)
   if (const char *u = std::getenv("GV_PAIR_MINB")) ctx->pair_minb = std::atoi(u);
   if (ctx->pair_minb < 3 || ctx->pair_minb > 6) ctx->pair_minb = GV_PAIR_MINB;
   if (const char *u = std::getenv("GV_SPAN_CHUNKS")) ctx->span_chunks_env = std::atoi(u);
+  if (const char *u = std::getenv("GV_WALK_SEG")) ctx->walk_seg = std::atoi(u);
+  if (ctx->walk_seg < 0 || ctx->walk_seg > 16384) ctx->walk_seg = 64;
   if (const char *u = std::getenv("GV_PAIR_WAVES")) ctx->pair_waves = std::atoi(u);
   if (ctx->pair_waves < 1 || ctx->pair_waves > 64) ctx->pair_waves = 32;
   if (ctx->fast_kind != 1) ctx->use_tma = false;

@@ -1011,17 +1011,24 @@ __global__ void __launch_bounds__(kThreads) k_sweep_walk(
   int32_t *__restrict__ miss, int32_t *__restrict__ missT, const SweepEntry *__restrict__ entries,
   unsigned *__restrict__ counters /* [1] batch count, [2] walk counter */,
   const int *__restrict__ batch_entry, const int *__restrict__ batch_mi,
-  const unsigned *__restrict__ batch_w, int sx, int sy, int nx, int ny, unsigned long long *__restrict__ stats)
+  const unsigned *__restrict__ batch_w, int sx, int sy, int nx, int ny, unsigned nseg, int seg,
+  unsigned long long *__restrict__ stats)
 {
+  // nseg > 1 (small sweeps: one scan): a batch is cut into nseg pieces of `seg` steps, each its own
+  // warp task, so that the longest lines are not walked by one warp from end to end (the critical
+  // path of a single 1000^2 scan); the state of the LineIterator after k0 steps has a closed form.
   const unsigned lane = threadIdx.x & 31;
   const unsigned nbatch = counters[1];
   unsigned long long st_physical = 0;
   for (;;) {
-    unsigned b = 0;
-    if (lane == 0) b = atomicAdd(counters + 2, 1u);
-    b = __shfl_sync(0xffffffffu, b, 0);
+    unsigned t = 0;
+    if (lane == 0) t = atomicAdd(counters + 2, 1u);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    const unsigned b = nseg > 1u ? t / nseg : t;
     if (b >= nbatch) break;
+    const int k0 = nseg > 1u ? (int)(t - b * nseg) * seg : 0;
     const SweepEntry E = entries[batch_entry[b]];
+    if (k0 >= E.D) continue;  // this batch's lines are shorter than the piece's start (warp-uniform)
     const int mi = batch_mi[(size_t)b * 32 + lane];
     const unsigned w = batch_w[(size_t)b * 32 + lane];
     const bool xmajor = E.dir < 2;
@@ -1047,8 +1054,18 @@ __global__ void __launch_bounds__(kThreads) k_sweep_walk(
     const unsigned mask_le = 0xffffffffu >> (31u - lane);
     const unsigned Pex = P - w;  // exclusive prefix
     unsigned st_phys32 = 0u;
+    int k1 = den;
+    if (nseg > 1u) {
+      // after k0 steps: num = (den/2 + k0*add) mod den, and the minor coordinate has advanced
+      // (den/2 + k0*add) div den times (add <= den: at most one minor step per major step)
+      const unsigned acc = (unsigned)num + (unsigned)k0 * (unsigned)add;  // < 2^31: k0, add <= 16384
+      const unsigned q = acc / (unsigned)den;
+      num = (int)(acc - q * (unsigned)den);
+      lin += k0 * dlin_major + (int)q * dlin_minor;
+      k1 = k0 + seg < den ? k0 + seg : den;
+    }
 #pragma unroll 1
-    for (int k = 0; k < den; ++k) {
+    for (int k = k0; k < k1; ++k) {
       // every lane is at the same major coordinate and the minor coordinates are monotone in the
       // lane index, so equal cells form contiguous lane runs: one RED per run (by its last lane),
       // the run's weight a difference of the warp prefix sums
