@@ -1,0 +1,147 @@
+"""CPU checks of the arithmetic k_points_pair (csrc/gv_points_pair.cuh) adds on top of the certified
+scheme of fast_point, on millions of samples and without a GPU:
+  1. fma(p, 1, c) rounds exactly like the separate add (the kernel's way of keeping ptxas from
+     contracting mul.rn.f32x2 + add.rn.f32x2): checked in binary64-emulated binary32;
+  2. the image test |RN(q - W/2)| against the thresholds of fill_pair_args (gv_api.cu) certifies
+     only what the interval [q - E(q), q + E(q)] certifies;
+  3. the tile taken from the bits of fma(q, 1/S, 192) is the tile of some pixel within 2^-16 tiles
+     of q: the 1-px dilation of the tile masks covers it;
+  4. the closed form k_sweep_walk uses to start a line piece after k0 steps;
+  5. the error budget of the 16.16 cell index with the 2-unit margin."""
+import numpy as np
+
+from oracle import gv_oracle as orc
+
+f32, f64 = np.float32, np.float64
+U22 = 2.0 ** -22
+
+
+def pair_thresholds(W, c):
+    """fill_pair_args for one axis (image size W, principal point c); all in double, rounded to the
+    safe side exactly like the host code."""
+    e6 = f64(f32(6.0) * f32(U22))
+    e0 = f64(f32(U22) * (f32(1.5) * abs(f32(c)) + f32(1.0)) * f32(1.0001))
+    half = 0.5 * W
+    e = f32(np.nextafter(f32((e6 * (W + 1.0) + e0) * 1.001), f32(np.inf)))
+    ain = f32(np.nextafter(f32(half - f64(e) - W * 2.0 ** -21), f32(0.0)))
+    aout = f32(np.nextafter(f32(((W + e0) / (1.0 - e6) - half) * (1.0 + 2.0 ** -21)), f32(np.inf)))
+    return e6, e0, f32(half), e, ain, aout
+
+
+def test_fma_with_one_equals_separate_add():
+    rng = np.random.default_rng(0)
+    n = 4_000_000
+    # products and addends of wildly different magnitudes, including cancellation
+    a = (rng.standard_normal(n) * np.exp(rng.uniform(-20, 20, n))).astype(f32)
+    b = (rng.standard_normal(n) * np.exp(rng.uniform(-20, 20, n))).astype(f32)
+    c = np.where(rng.random(n) < 0.3, -(a.astype(f64) * b.astype(f64)), rng.standard_normal(n) * np.exp(rng.uniform(-20, 20, n))).astype(f32)
+    p = (a * b).astype(f32)                                  # mul.rn: one rounding
+    sep = (p + c).astype(f32)                                # add.rn: one rounding
+    fused = (p.astype(f64) * 1.0 + c.astype(f64)).astype(f32)  # fma(p, 1, c): p*1 exact, p + c exact in double, one rounding
+    assert np.array_equal(sep.view(np.uint32), fused.view(np.uint32))
+    # and it differs from the contracted fma(a, b, c) often enough that a contraction would show
+    contracted = (a.astype(f64) * b.astype(f64) + c.astype(f64)).astype(f32)
+    assert (contracted.view(np.uint32) != sep.view(np.uint32)).mean() > 0.05
+
+
+def test_image_thresholds_certify_only_what_the_interval_does():
+    for W, c in ((416.0, 208.0), (640.0, 321.5), (1280.0, 600.25), (64.0, 10.0)):
+        e6, e0, half, e, ain, aout = pair_thresholds(W, c)
+        rng = np.random.default_rng(int(W))
+        q = np.concatenate([
+            rng.uniform(-3 * W, 4 * W, 1_000_000),
+            rng.normal(0.0, 2e-3, 500_000), W + rng.normal(0.0, 2e-3, 500_000),   # both image edges
+            np.array([0.0, W, -0.0, np.nextafter(W, 0.0), 1e30, -1e30]),
+        ]).astype(f32)
+        E = np.abs(q.astype(f64)) * e6 + e0                   # the proven interval half-width
+        lo, hi = q.astype(f64) - E, q.astype(f64) + E
+        inside_all = (lo >= 0.0) & (hi < W)                   # every value of the interval is in [0, W)
+        outside_all = (hi < 0.0) | (lo >= W)
+        with np.errstate(invalid="ignore"):
+            d = np.abs((q - half).astype(f32))                # |RN(q - W/2)| as the kernel computes it
+        cert_in, cert_out = d < ain, d > aout
+        assert not np.any(cert_in & ~inside_all), (W, c)
+        assert not np.any(cert_out & ~outside_all), (W, c)
+        # inside the image the constant margin dominates the proven one
+        assert np.all(f64(e) >= E[cert_in])
+        # an overflowed projection (q = +-Inf) is certainly outside, NaN is neither (-> deferred)
+        with np.errstate(invalid="ignore"):
+            dinf = np.abs((np.array([np.inf, -np.inf, np.nan], f32) - half).astype(f32))
+        assert list(dinf > aout) == [True, True, False] and not np.any(dinf < ain)
+        # and the band left to the exact pass is thin
+        band = ~(cert_in | cert_out)
+        assert band[:1_000_000].mean() < 1e-4
+
+
+def test_tile_from_float_bits_is_within_the_dilation():
+    rng = np.random.default_rng(1)
+    for shift in (4, 5, 6):
+        S = float(1 << shift)
+        W = 13.0 * S if shift == 5 else 16.0 * S
+        q = np.concatenate([rng.uniform(1e-3, W - 1e-3, 2_000_000),
+                            (np.arange(1, int(W / S)) * S)[None, :].repeat(2000, 0).ravel() + rng.normal(0, 1e-3, 2000 * (int(W / S) - 1))]).astype(f32)
+        q = q[(q > 1e-3) & (q < W - 1e-3)]
+        t = (q.astype(f64) * (1.0 / S) + 192.0).astype(f32)   # fma: exact product, one rounding
+        tile = (t.view(np.uint32) >> 16).astype(np.int64) - 0x4340
+        assert tile.min() >= 0 and tile.max() <= int(np.ceil(W / S)) - 1 + 1
+        # the tile's pixel range, widened by 1 px, contains q
+        assert np.all((q.astype(f64) >= tile * S - 1.0) & (q.astype(f64) < (tile + 1) * S + 1.0))
+        # in fact it is off by at most 2^-16 tiles
+        assert np.all(np.abs((tile + 0.5) * S - q.astype(f64)) <= 0.5 * S + S * 2.0 ** -16)
+
+
+def test_line_piece_start_closed_form():
+    """State of the grid_map LineIterator after k0 steps, as k_sweep_walk computes it for a piece."""
+    rng = np.random.default_rng(3)
+    for _ in range(400):
+        sx, sy, ex, ey = (int(v) for v in rng.integers(-300, 300, 4))
+        dx, dy = abs(ex - sx), abs(ey - sy)
+        den, add = max(dx, dy), min(dx, dy)
+        if den == 0:
+            continue
+        line = orc.bresenham_cells(sx, sy, ex, ey)
+        xmajor = dx >= dy
+        for k0 in (0, 1, den // 3, den - 1, int(rng.integers(0, den))):
+            acc = den // 2 + k0 * add
+            q, num = acc // den, acc % den
+            smaj = (1 if ex >= sx else -1) if xmajor else (1 if ey >= sy else -1)
+            smin = (1 if ey >= sy else -1) if xmajor else (1 if ex >= sx else -1)
+            major = (sx if xmajor else sy) + smaj * k0
+            minor = (sy if xmajor else sx) + smin * q
+            cell = (major, minor) if xmajor else (minor, major)
+            assert tuple(line[k0]) == cell
+            # and the iteration continues identically from (num, cell)
+            n2, mn = num, minor
+            for k in range(k0, min(den, k0 + 5)):
+                exp = line[k]
+                got = ((sx if xmajor else sy) + smaj * k, mn) if xmajor else (mn, (sx if xmajor else sy) + smaj * k)
+                assert tuple(exp) == got
+                n2 += add
+                if n2 >= den:
+                    n2 -= den
+                    mn += smin
+
+
+def test_index_margin_budget():
+    """16.16 index: the fixed-point value is within 1.03 units of the exact coordinate, so a margin
+    of 2 units certifies.  Emulated in double for the maps of BASELINE configs 3 and 5."""
+    rng = np.random.default_rng(4)
+    for n_cells, res, reach in ((2048, 0.1, 1204), (8192, 0.05, 2404), (1000, 0.05, 0)):
+        half = 0.5 * n_cells * res
+        bias = reach if reach else 16
+        magic = 1.5 * 2.0 ** 36
+        C = f64(half / res + bias + magic)
+        nires = f64(-1.0 / res)
+        pad = min(3.0, (bias - 2) * res)   # stay where the biased coordinate is positive (the kernel checks the high word)
+        p = rng.uniform(-half - pad, half + pad, 1_000_000).astype(f32)
+        # fma in double: the product and the sum carried in extended precision, one rounding to double
+        ld = np.longdouble
+        r = (p.astype(ld) * ld(nires) + ld(C)).astype(f64)
+        k = (r.view(np.uint64) & 0xFFFFFFFF).astype(np.int64) - (bias << 16)
+        exact = (half - p.astype(ld)) / ld(res)                # index coordinate, extended precision
+        err_units = np.abs(k.astype(ld) - exact * 65536.0)
+        assert float(err_units.max()) < 1.03
+        # a fraction in [2, 65534) therefore never disagrees with floor(exact)
+        frac = k & 0xFFFF
+        ok = (frac >= 2) & (frac < 65534)
+        assert np.array_equal((k[ok] >> 16), np.floor(exact[ok]).astype(np.int64))
