@@ -80,6 +80,7 @@ struct gv_ctx {
                         // only slows the binning kernel down by what it gains)
   unsigned long long merges = 0;
   unsigned *d_list_count = nullptr;  // work-item counter of the raycast sweep
+  bool list_count_dirty = true;      // the counters are not known to be zero
   SweepEntry *d_sweep = nullptr;     // sweep table for the current start cell
   unsigned *d_sweep_prefix = nullptr;  // [n_sweep+1] first work item of each entry
   int *d_sweep_item = nullptr;         // [n_sweep_items] entry of each work item
@@ -365,8 +366,12 @@ int scan_u32(gv_ctx *ctx, unsigned *d, unsigned long long n, int level)
   return GV_OK;
 }
 
-int upload_boxes(gv_ctx *ctx, const gv_box *boxes, int nboxes, bool on_device, float4 **out)
+// raw_out != NULL: the rounding is left to the caller's k_box_masks launch (the device copy of the
+// raw records is returned), one launch less
+int upload_boxes(gv_ctx *ctx, const gv_box *boxes, int nboxes, bool on_device, float4 **out,
+                 const BoxRaw **raw_out = nullptr)
 {
+  if (raw_out) *raw_out = nullptr;
   static_assert(sizeof(gv_box) == 40 && sizeof(BoxRaw) == 40, "BoundingBox layout");
   float4 *d_f4 = nullptr;
   GV_TRY(reserve_t(ctx, S_BOX_F4, (size_t)(nboxes > 0 ? nboxes : 1), &d_f4));
@@ -379,8 +384,12 @@ int upload_boxes(gv_ctx *ctx, const gv_box *boxes, int nboxes, bool on_device, f
                               ctx->stream));
       d_raw = tmp;
     }
-    k_round_boxes<<<blocks_for(nboxes, 256), 256, 0, ctx->stream>>>(d_raw, nboxes, d_f4);
-    GV_LAUNCH_CHECK();
+    if (raw_out) {
+      *raw_out = d_raw;
+    } else {
+      k_round_boxes<<<blocks_for(nboxes, 256), 256, 0, ctx->stream>>>(d_raw, nboxes, d_f4);
+      GV_LAUNCH_CHECK();
+    }
   }
   *out = d_f4;
   return GV_OK;
@@ -527,7 +536,7 @@ int fuse_dev_impl(gv_ctx *ctx, const float *d_x, const float *d_y, const float *
     int sh, tx, ty;
     mask_geometry(a.cam[c].W, a.cam[c].H, &sh, &tx, &ty);
     k_box_masks<<<1, kThreads, 0, ctx->stream>>>(d_f4, d_set_off + c, sh, tx, ty, a.mask_words,
-                                                 a.mask_stride, 0, d_masks + (size_t)c * a.mask_stride);
+                                                 a.mask_stride, 0, d_masks + (size_t)c * a.mask_stride, nullptr, nullptr);
     GV_LAUNCH_CHECK();
   }
   GV_CUDA(cudaStreamSynchronize(ctx->stream));  // set_off is a host temporary
@@ -574,7 +583,10 @@ int raycast_flush_impl(gv_ctx *ctx, unsigned rank, unsigned world, bool p2p_gath
   if (!ctx->ends_dirty) return GV_OK;
   ctx->ends_dirty = false;
   if (!ctx->bin.origin_ok || ctx->n_sweep_items == 0) return GV_OK;  // nothing was binned
-  GV_CUDA(cudaMemsetAsync(ctx->d_list_count, 0, 4 * sizeof(unsigned), ctx->stream));
+  // the sweep's counters are left zero by its last kernel (k_miss_fold); memset only at the first
+  // sweep or after one that was cut short by an error
+  if (ctx->list_count_dirty) GV_CUDA(cudaMemsetAsync(ctx->d_list_count, 0, 4 * sizeof(unsigned), ctx->stream));
+  ctx->list_count_dirty = true;
   const unsigned nb = (unsigned)ctx->num_sms * 8u;
   // batch list: every non-empty cell once, each span padded to a multiple of 32
   const size_t max_batches = ctx->ncells / 32 + (size_t)ctx->n_sweep_items + 1;
@@ -647,8 +659,10 @@ int raycast_flush_impl(gv_ctx *ctx, unsigned rank, unsigned world, bool p2p_gath
     }
     if (x1 >= x0 && y1 >= y0) {
       const dim3 grid((unsigned)((x1 - x0) / 32 + 1), (unsigned)((y1 - y0) / 32 + 1));
-      k_miss_fold<<<grid, 256, 0, ctx->stream>>>(ctx->d_miss, ctx->d_missT, ctx->g.nx, ctx->g.ny, x0, y0, x1, y1);
+      k_miss_fold<<<grid, 256, 0, ctx->stream>>>(ctx->d_miss, ctx->d_missT, ctx->g.nx, ctx->g.ny, x0, y0, x1, y1,
+                                                 ctx->d_list_count);
       GV_LAUNCH_CHECK();
+      ctx->list_count_dirty = false;
     }
     ctx->sweep_reach = 0.0;
   }
@@ -1996,13 +2010,17 @@ static int launch_deferred(gv_ctx *ctx, const FastArgs &f, unsigned long long nw
   // per scan CTA: room for 1/4 of its words to be non-zero (the certified paths defer < 1 % of the
   // points); what does not fit is processed in place
   const unsigned long long per_cta = (nwords + nb - 1) / nb;
-  dl.capacity = (unsigned)(per_cta / 4 + 64);
-  GV_TRY(reserve_t(ctx, S_DEFER_LIST, (size_t)nb * dl.capacity, &dl.items));
+  // a scan or two (<= 16 k words): the scan processes its words in place (capacity 0), one launch less
+  const bool in_place = nwords <= 16384ull;
+  dl.capacity = in_place ? 0u : (unsigned)(per_cta / 4 + 64);
+  GV_TRY(reserve_t(ctx, S_DEFER_LIST, (size_t)nb * (dl.capacity ? dl.capacity : 1u), &dl.items));
   GV_TRY(reserve_t(ctx, S_DEFER_COUNT, (size_t)nb, &dl.count));
   k_points_deferred<<<nb, kThreads, 0, ctx->stream>>>(f, dl);
   GV_LAUNCH_CHECK();
-  k_points_deferred_list<<<nb, kThreads, 0, ctx->stream>>>(f, dl, ctx->d_stats + 4);
-  GV_LAUNCH_CHECK();
+  if (!in_place) {
+    k_points_deferred_list<<<nb, kThreads, 0, ctx->stream>>>(f, dl, ctx->d_stats + 4);
+    GV_LAUNCH_CHECK();
+  }
   return GV_OK;
 }
 
@@ -2339,7 +2357,8 @@ static int process_batch_impl(gv_ctx *ctx, const float *px, const float *py, con
     ctx->c_valid = true;
   }
   float4 *d_f4 = nullptr;
-  GV_TRY(upload_boxes(ctx, boxes, nboxes, boxes_on_device, &d_f4));
+  const BoxRaw *d_raw = nullptr;  // non-NULL: k_box_masks rounds the boxes itself (sets of <= 256 boxes)
+  GV_TRY(upload_boxes(ctx, boxes, nboxes, boxes_on_device, &d_f4, max_boxes <= kThreads ? &d_raw : nullptr));
   // per-frame image-tile box masks
   int mty;
   mask_geometry(ctx->cam[0].W, ctx->cam[0].H, &a.mask_shift[0], &a.mask_tx[0], &mty);
@@ -2351,7 +2370,7 @@ static int process_batch_impl(gv_ctx *ctx, const float *px, const float *py, con
   const bool fast = fast_eligible(ctx, a.bin, max_boxes);
   k_box_masks<<<nframes, kThreads, 0, ctx->stream>>>(d_f4, d_boff, a.mask_shift[0], a.mask_tx[0],
                                                     mty, a.mask_words, a.mask_stride, fast ? 1 : 0,
-                                                    d_masks);
+                                                    d_masks, d_raw, d_f4);
   GV_LAUNCH_CHECK();
   a.masks = d_masks;
   a.tile_pts = tile_pts;

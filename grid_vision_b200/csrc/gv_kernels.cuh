@@ -570,6 +570,20 @@ __global__ void __launch_bounds__(kThreads) k_points(const __grid_constant__ Poi
   }
 }
 
+struct BoxRaw {  // ref: include/grid_vision/object_detection.hpp:27-32 (40 bytes)
+  double x_min, y_min, x_max, y_max;
+  float confidence;
+  int label;
+};
+
+// double bounds -> float so that float compares decide exactly like the reference's float-vs-double
+// compares: x_min, y_min round up, x_max, y_max round down (k_round_boxes, k_box_masks)
+__device__ __forceinline__ float4 round_box(const BoxRaw &b)
+{
+  return make_float4(__double2float_ru(b.x_min), __double2float_ru(b.y_min), __double2float_rd(b.x_max),
+                     __double2float_rd(b.y_max));
+}
+
 // Image-tile prefilter for the box test.  One CTA per box set (a camera, or a frame in batch
 // mode); bit b of masks[set][tile*words + b/64] is set iff box b (index local to the set)
 // overlaps the tile's pixel square [tx*S, (tx+1)*S) x [ty*S, (ty+1)*S), S = 2^shift.
@@ -582,15 +596,26 @@ __global__ void __launch_bounds__(kThreads) k_box_masks(const float4 *__restrict
                                                         const int *__restrict__ set_offsets,
                                                         int shift, int tiles_x, int tiles_y,
                                                         int words, int stride, int rev32,
-                                                        unsigned long long *__restrict__ masks)
+                                                        unsigned long long *__restrict__ masks,
+                                                        const BoxRaw *__restrict__ raw, float4 *boxes_out)
 {
   const int set = blockIdx.x;
   const int b0 = set_offsets[set], b1 = set_offsets[set + 1];
   const float S = (float)(1 << shift), D = rev32 ? 1.0f : 0.0f;
-  // the usual set (<= 256 boxes) is staged in shared memory once: every tile tests every box
+  // the usual set (<= 256 boxes) is staged in shared memory once: every tile tests every box.
+  // raw != NULL (sets of <= 256 boxes only, host-checked): this CTA also does k_round_boxes' job
+  // for its set, one launch less per batch.
   __shared__ float4 s_b[kThreads];
   const bool staged = b1 - b0 <= kThreads;
-  if (staged && b0 + (int)threadIdx.x < b1) s_b[threadIdx.x] = boxes[b0 + threadIdx.x];
+  if (staged && b0 + (int)threadIdx.x < b1) {
+    if (raw) {
+      const float4 B = round_box(raw[b0 + threadIdx.x]);
+      s_b[threadIdx.x] = B;
+      boxes_out[b0 + threadIdx.x] = B;
+    } else {
+      s_b[threadIdx.x] = boxes[b0 + threadIdx.x];
+    }
+  }
   __syncthreads();
   for (int t = threadIdx.x; t < tiles_x * tiles_y * words; t += kThreads) {
     const int w = t % words, tile = t / words;
@@ -1094,9 +1119,11 @@ __global__ void __launch_bounds__(kThreads) k_sweep_walk(
 // lines can reach, and missT is zero again.  32 x 32 tiles through shared memory: both planes are
 // read and written in 128-byte rows.  Runs after k_sweep_walk on the same stream: plain adds.
 __global__ void __launch_bounds__(256) k_miss_fold(int32_t *__restrict__ miss, int32_t *__restrict__ missT, int nx,
-                                                   int ny, int x0, int y0, int x1, int y1)
+                                                   int ny, int x0, int y0, int x1, int y1, unsigned *__restrict__ counters)
 {
   __shared__ int t[32][33];
+  // last kernel of a sweep: leave the sweep's work counters zero for the next one
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 4) counters[threadIdx.x] = 0u;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int bx = x0 + (int)blockIdx.x * 32, by = y0 + (int)blockIdx.y * 32;
   bool any = false;
@@ -1779,18 +1806,11 @@ __global__ void __launch_bounds__(kThreads) k_n2_box(
 // bounds, inclusive.  u >= x_min  <=>  u >= RU_f32(x_min)  and  u <= x_max  <=>  u <= RD_f32(x_max)
 // for every float u, so rounding the bounds once (toward +inf for mins, -inf for maxes) turns
 // the per-point double compares into exact float compares.  NaN bounds stay NaN (never match).
-struct BoxRaw {  // ref: include/grid_vision/object_detection.hpp:27-32 (40 bytes)
-  double x_min, y_min, x_max, y_max;
-  float confidence;
-  int label;
-};
-
 __global__ void k_round_boxes(const BoxRaw *__restrict__ in, int n, float4 *__restrict__ out)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  out[i] = make_float4(__double2float_ru(in[i].x_min), __double2float_ru(in[i].y_min),
-                       __double2float_rd(in[i].x_max), __double2float_rd(in[i].y_max));
+  out[i] = round_box(in[i]);
 }
 
 // ----------------------------------------------------------------------------------

@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest gpu exit $?"; tail -3 gpurun_out/pytest_gpu.log
-for sg in 0 64 128 32; do
+for sg in 64; do
   GV_WALK_SEG=$sg python - <<'PY'
 import os, sys, numpy as np, torch
 sys.path.insert(0, '.')
