@@ -59,12 +59,17 @@ def main():
         name = r[kn].split("(")[0]
         tot[name] = tot.get(name, 0.0) + float(r[mv].replace(",", ""))
         cnt[name] += 1
-    total = sum(tot.values())
+    # the atomic micro-benchmark (k_mb_*, run once before the steps) is not part of a step
+    step = {k: v for k, v in tot.items() if "k_mb_" not in k}
+    total = sum(step.values())
     md += ["## launch list (`--metrics gpu__time_duration.sum --clock-control none`)", "",
-           "Per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes.", "",
-           "| kernel | launches | total ns | share |", "|---|---|---|---|"]
+           "Per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes.",
+           "Shares are of the product kernels' total (the atomic micro-benchmark `k_mb_*`, which `bench.py` runs once",
+           "outside the timed region, is listed without a share).", "",
+           "| kernel | launches | total ns | share of the steps |", "|---|---|---|---|"]
     for name, v in sorted(tot.items(), key=lambda kv: -kv[1]):
-        md.append(f"| `{name}` | {cnt[name]} | {v:.0f} | {100 * v / total:.1f}% |")
+        share = f"{100 * v / total:.1f}%" if name in step else "—"
+        md.append(f"| `{name}` | {cnt[name]} | {v:.0f} | {share} |")
     open(out, "w").write("\n".join(md) + "\n")
 
 
