@@ -288,7 +288,18 @@ GV_API int gv_grid_finalize(gv_ctx *ctx, int32_t k_decay, const double *corners,
  * transform -> project -> label (camera 0, per-frame box lists) -> base transform -> cell
  * -> bin, in ONE kernel that reads each point once.  frame_offsets[nframes+1] delimit the
  * frames in the point planes, box_frame_offsets[nframes+1] delimit each frame's boxes.
- * labels_out (n int16) is nullable.  Follow with gv_grid_finalize. */
+ * labels_out (n int16) is nullable.  Follow with gv_grid_finalize.
+ * Performance notes (results are identical either way):
+ *  - one sensor pose per raycast: all beams binned between two sweeps share the start cell, so a
+ *    moving ego needs gv_set_base_transform (which sweeps what was binned) per pose: batch scans
+ *    that share a pose, a pose change costs one sweep;
+ *  - the fastest kernel (two points per thread) needs every frame offset and size to be even, the
+ *    planes 8-byte and labels_out 4-byte aligned, one camera with an extrinsic, canonical K and at
+ *    most 64 boxes per frame; other layouts take the one-point-per-thread kernel, other
+ *    configurations the generic one;
+ *  - the _dev entry point runs asynchronously on the context stream (a private non-blocking stream
+ *    unless gv_set_stream was called): order it against the producers of its inputs and the
+ *    consumers of its outputs with that stream. */
 GV_API int gv_process_batch(gv_ctx *ctx, const float *x, const float *y, const float *z,
                             const uint64_t *frame_offsets, int nframes, const gv_box *boxes,
                             const int32_t *box_frame_offsets, const gv_accum_params *prm,
