@@ -139,21 +139,24 @@ __device__ __forceinline__ void label_pair(const Boxes &bsrc, unsigned long long
   const float rl0 = lo2(rl), rl1 = hi2(rl), rh0 = lo2(rh), rh1 = hi2(rh);
   unsigned mw = (unsigned)mu;
   unsigned base = 0;
-#pragma unroll 1
-  for (;;) {
+  // next candidate in list order: byte offset of its box, or false when the masks are exhausted
+  auto next = [&](unsigned &off) -> bool {
     if (mw == 0u) {
-      if (base) break;
+      if (base) return false;
       base = 32u * 16u;
       mw = (unsigned)(mu >> 32);
-      if (mw == 0u) break;
+      if (mw == 0u) return false;
     }
     const unsigned p = (unsigned)__clz((int)mw);
     mw &= ~(0x80000000u >> p);
-    const float4 B = bsrc.box_at(base + 16u * p);
+    off = base + 16u * p;
+    return true;
+  };
+  auto test = [&](const float4 B, unsigned off) -> bool {  // true: both lanes are settled
     const bool o0 = !pend0 | (qh0 < B.x) | (ql0 > B.z) | (rh0 < B.y) | (rl0 > B.w);  // certainly outside this box
     const bool o1 = !pend1 | (qh1 < B.x) | (ql1 > B.z) | (rh1 < B.y) | (rl1 > B.w);
     if (!(o0 & o1)) {
-      const int id = (int)((base >> 4) + p);
+      const int id = (int)(off >> 4);
       if (!o0) {
         if ((ql0 >= B.x) & (qh0 <= B.z) & (rl0 >= B.y) & (rh0 <= B.w)) lab0 = id;
         else def |= 1u;
@@ -164,9 +167,16 @@ __device__ __forceinline__ void label_pair(const Boxes &bsrc, unsigned long long
         else def |= 2u;
         pend1 = false;
       }
-      if (!(pend0 | pend1)) break;
+      return !(pend0 | pend1);
     }
-  }
+    return false;
+  };
+  // (Prefetching the next candidate's box while this one is tested was measured: the five extra live
+  // registers spill in the main loop under the 48-register budget, 2.81 -> 3.24 ms.)
+  unsigned off;
+#pragma unroll 1
+  while (next(off))
+    if (test(bsrc.box_at(off), off)) break;
 }
 
 // end cell of one lane whose certified index did not say "inside" (same code as fast_point)
