@@ -62,12 +62,26 @@ def measured_peak_gbs():
 
 # --------------------------------------------------------------------------- clocks
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region: NVML in-process every 2 ms
+    (the timed region of the default run is ~35 ms: `nvidia-smi -lms` needs longer than that just to
+    start), `nvidia-smi -lms 20` as the fallback."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
-        self.rows, self.proc = [], None
+        self.rows, self.proc, self.nv, self._stop = [], None, None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(int(index))
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            self.nv = (pynvml, h)
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nv = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
@@ -77,6 +91,26 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv, h = self.nv
+        bits = (("hw_slowdown", getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8)),
+                ("hw_thermal_slowdown", getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)),
+                ("sw_thermal_slowdown", getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)),
+                ("sw_power_cap", getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)))
+        try:
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        except Exception:
+            mx = 0
+        while not self._stop:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                flags = ["Active" if r & b else "Not Active" for _, b in bits]
+                self.rows.append((time.time(), ",".join([str(sm), str(mx), "0"] + flags)))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
@@ -85,13 +119,20 @@ class ClockSampler:
         return time.time()
 
     def stop(self, t0=None, t1=None):
-        if not self.proc:
+        if not self.proc and not self.nv:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
+        if self.nv:
+            self._stop = True
+            self.t.join(timeout=1.0)
+        else:
+            time.sleep(0.15)
+            self.proc.terminate()
         sm, mx, reasons = [], [], set()
         for ts, line in self.rows:
-            if t0 is not None and not (t0 - 0.05 <= ts <= t1 + 0.15):
+            # NVML rows are time-stamped where they are taken: keep the timed region only;
+            # nvidia-smi's rows arrive late and sparsely: a wider window
+            pre, post = (0.0, 0.004) if self.nv else (0.05, 0.15)
+            if t0 is not None and not (t0 - pre <= ts <= t1 + post):
                 continue
             f = [s.strip() for s in line.split(",")]
             if len(f) < 7:
@@ -107,6 +148,7 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": max(mx) if mx else None, "samples": len(sm),
+                "source": "nvml, 2 ms poll" if self.nv else "nvidia-smi -lms 20",
                 "reasons": sorted(reasons)}
 
 
