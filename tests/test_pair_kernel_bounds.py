@@ -145,3 +145,74 @@ def test_index_margin_budget():
         frac = k & 0xFFFF
         ok = (frac >= 2) & (frac < 65534)
         assert np.array_equal((k[ok] >> 16), np.floor(exact[ok]).astype(np.int64))
+
+
+def test_pair_label_walk_certified_labels_are_the_oracles():
+    """numpy emulation of k_points_pair's label decision (binary32 projection with the kernel's
+    operation order, tile from the float bits, 1-px dilated tile masks, candidate walk with the
+    constant margin): whenever the emulation does not defer, its label is the oracle's, and it
+    defers rarely.  Checked on full C1 scans with integer-valued and with fractional boxes."""
+    from grid_vision_b200 import synth
+    wl = synth.C1
+    S, shift = 32.0, 5
+    tiles_x = (wl.image_w + 31) >> shift
+    W, H = float(wl.image_w), float(wl.image_h)
+    e6, e0u, half_w, eu, ain_u, aout_u = pair_thresholds(W, wl.cx)
+    _, e0v, half_h, ev, ain_v, aout_v = pair_thresholds(H, wl.cy)
+    Tc = synth.camera_extrinsics(1)[0]
+    rng = np.random.default_rng(11)
+    deferred = total_in = 0
+    for frame, fractional in ((0, False), (1, True), (2, False)):
+        xyz = synth.make_scans(wl, frame0=frame, frames=1).numpy()
+        boxes = synth.make_boxes(wl, frame=frame, n=50)
+        if fractional:
+            for k in ("x_min", "y_min"):
+                boxes[k] += rng.uniform(0, 1, len(boxes))
+            for k in ("x_max", "y_max"):
+                boxes[k] -= rng.uniform(0, 1, len(boxes))
+        X, Y, Z = orc.transform_points(Tc, *xyz)
+        elab, _, _, _ = orc.project_label(wl.K(), wl.image_w, wl.image_h, X, Y, Z, boxes)
+        with np.errstate(all="ignore"):
+            fr = Z > f32(0.001)
+            rz = (f32(1.0) / Z).astype(f32)                       # rcp.approx: within 1 ulp; exact is one instance
+            t = (X * rz).astype(f32)
+            q = (f64(f32(wl.fx)) * t.astype(f64) + f64(f32(wl.cx))).astype(f32)   # fma: one rounding
+            t = (Y * rz).astype(f32)
+            r = (f64(f32(wl.fy)) * t.astype(f64) + f64(f32(wl.cy))).astype(f32)
+            aq, ar = np.abs((q - half_w).astype(f32)), np.abs((r - half_h).astype(f32))
+        inn = fr & (aq < ain_u) & (ar < ain_v)
+        defer = fr & ~inn & ~((aq > aout_u) | (ar > aout_v))
+        lab = np.full(q.shape, -1, np.int64)
+        # rounded float bounds (k_round_boxes) and 1-px dilated tile masks (k_box_masks, rev32 mode)
+        bx0 = np.nextafter(boxes["x_min"].astype(f32), f32(np.inf), where=boxes["x_min"].astype(f32) < boxes["x_min"], out=boxes["x_min"].astype(f32))
+        by0 = np.nextafter(boxes["y_min"].astype(f32), f32(np.inf), where=boxes["y_min"].astype(f32) < boxes["y_min"], out=boxes["y_min"].astype(f32))
+        bx1 = np.nextafter(boxes["x_max"].astype(f32), f32(-np.inf), where=boxes["x_max"].astype(f32) > boxes["x_max"], out=boxes["x_max"].astype(f32))
+        by1 = np.nextafter(boxes["y_max"].astype(f32), f32(-np.inf), where=boxes["y_max"].astype(f32) > boxes["y_max"], out=boxes["y_max"].astype(f32))
+        idx = np.flatnonzero(inn)
+        qi, ri = q[idx], r[idx]
+        tu = ((qi.astype(f64) / S + 192.0).astype(f32).view(np.uint32) >> 16).astype(np.int64) - 0x4340
+        tv = ((ri.astype(f64) / S + 192.0).astype(f32).view(np.uint32) >> 16).astype(np.int64) - 0x4340
+        assert tu.min() >= 0 and tu.max() < tiles_x and tv.min() >= 0 and tv.max() < tiles_x
+        x0t, y0t = tu * S, tv * S
+        ql, qh = (qi - eu).astype(f32), (qi + eu).astype(f32)
+        rl, rh = (ri - ev).astype(f32), (ri + ev).astype(f32)
+        pend = np.ones(idx.size, bool)
+        li = np.full(idx.size, -1, np.int64)
+        di = np.zeros(idx.size, bool)
+        for b in range(len(boxes)):       # list order = candidate order
+            cand = (bx1[b] >= x0t - 1) & (bx0[b] < x0t + S + 1) & (by1[b] >= y0t - 1) & (by0[b] < y0t + S + 1)
+            out = (qh < bx0[b]) | (ql > bx1[b]) | (rh < by0[b]) | (rl > by1[b])
+            ins = (ql >= bx0[b]) & (qh <= bx1[b]) & (rl >= by0[b]) & (rh <= by1[b])
+            # a box outside the point's (dilated) tile mask is never even looked at: it must be certainly outside
+            assert not np.any(pend & ~cand & ~out)
+            hit = pend & cand & ~out
+            li[hit & ins] = b
+            di[hit & ~ins] = True
+            pend &= ~hit
+        lab[idx] = li
+        defer[idx] |= di
+        keep = ~defer
+        assert np.array_equal(lab[keep], elab[keep].astype(np.int64)), f"frame {frame}"
+        deferred += int(defer.sum())
+        total_in += int(inn.sum())
+    assert total_in > 50_000 and deferred < 0.01 * total_in
