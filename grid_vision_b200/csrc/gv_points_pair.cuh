@@ -238,7 +238,9 @@ __device__ __forceinline__ void pair_body(const FastArgs &a, const PairArgs &pa,
   // below is NaN or +Inf.  r2 = NaN drops the beam (X1); r2 >= 1e30 (Inf, or a finite coordinate
   // large enough to threaten overflow: |T| < 1e6 is host-checked, so r2 < 1e30 bounds |x|, |y| of
   // the base frame) defers the point.  A huge z alone leaves r2 small; it can only make the
-  // camera rows overflow, which turns q or r into Inf/NaN and fails both image tests: deferred.
+  // camera rows or the projection overflow: the rows are the reference's own arithmetic (same
+  // NaN / Inf), an infinite q or r is certainly outside the image as it is in the reference, and a
+  // NaN q or r fails both image tests: deferred.
   unsigned def = 0u;  // bit 0 / 1: the even / odd point is deferred to k_points_deferred
 
   // ---------------- camera: depth row first.  Ends with the image-tile mask loads in flight; the
