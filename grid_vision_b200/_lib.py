@@ -52,7 +52,7 @@ class Stats(C.Structure):
 EXPORTS = [
     "gv_version", "gv_status_string", "gv_create", "gv_destroy", "gv_last_error",
     "gv_synchronize", "gv_join", "gv_stream", "gv_set_stream", "gv_get_stats",
-    "gv_graph_begin", "gv_graph_end", "gv_graph_launch", "gv_graph_destroy",
+    "gv_graph_begin", "gv_graph_end", "gv_graph_launch", "gv_graph_destroy", "gv_debug_pair_thresholds",
     "gv_set_cameras", "gv_fuse", "gv_fuse_aos32", "gv_fuse_dev", "gv_transform_points",
     "gv_project_kdtree", "gv_partition_by_label", "gv_segment_ground", "gv_bbox_pose",
     "gv_box_depths", "gv_pixels_to_3d",

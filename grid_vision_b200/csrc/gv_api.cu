@@ -1130,6 +1130,24 @@ int gv_set_stream(gv_ctx *ctx, void *stream)
   return GV_OK;
 }
 
+static void pair_axis_thresholds(double W, double e6, double e0, float *half_out, float *e_out, float *ain, float *aout);
+
+// Host-only probe (no device, no context): the thresholds k_points_pair's certified image test uses
+// for an image axis of `size` pixels with principal point c, exactly as fill_fast_args /
+// fill_pair_args compute them.  out = {half, e, ain, aout, e6, e0}.  The CPU tests check the error
+// analysis against these very numbers (tests/test_pair_kernel_bounds.py).
+int gv_debug_pair_thresholds(double size, float c, float *out)
+{
+  if (!out || !(size > 0.0)) return GV_ERR_INVALID;
+  const float u22 = 2.384185791015625e-07f;
+  const float e6 = 6.0f * u22;
+  const float e0 = u22 * (1.5f * std::fabs(c) + 1.0f) * 1.0001f;
+  pair_axis_thresholds((double)(float)size, (double)e6, (double)e0, &out[0], &out[1], &out[2], &out[3]);
+  out[4] = e6;
+  out[5] = e0;
+  return GV_OK;
+}
+
 // ---- CUDA graphs: a captured sequence of device-pointer calls replayed with one launch ----
 int gv_graph_begin(gv_ctx *ctx)
 {
@@ -2102,6 +2120,21 @@ static int launch_points_fast(gv_ctx *ctx, FastArgs &f, bool bounded, bool tma, 
 // Thresholds of k_points_pair's certified image test and the constants of its tile lookup, from
 // E(q) = e6 |q| + e0 (fill_fast_args).  Everything is worked out in double and rounded to the
 // safe side: a threshold that is too strict only defers a few more points.
+// One image axis of size W with E(q) = e6 |q| + e0: image centre, the constant interval half-width
+// of the box tests and the two thresholds of the certified image test (see fill_pair_args).
+static void pair_axis_thresholds(double W, double e6, double e0, float *half_out, float *e_out, float *ain, float *aout)
+{
+  const double slack = 1.0 + 4.76837158203125e-07;  // 1 + 2^-21
+  const double half = 0.5 * W;                        // exact in binary32 (W is an image size)
+  const double e = (e6 * (W + 1.0) + e0) * 1.001;     // >= E(q) for every |q| <= W + 1
+  *half_out = (float)half;
+  *e_out = std::nextafterf((float)e, INFINITY);
+  // |RN(q - W/2)| < ain  =>  E < q < W - E, hence every value within E(q) of q is in [0, W)
+  *ain = std::nextafterf((float)(half - (double)*e_out - W * 4.76837158203125e-07), 0.0f);
+  // |RN(q - W/2)| > aout  =>  q - E(q) >= W or q + E(q) < 0
+  *aout = std::nextafterf((float)(((W + e0) / (1.0 - e6) - half) * slack), INFINITY);
+}
+
 static void fill_pair_args(const FastArgs &f, PairArgs &p)
 {
   memset(&p, 0, sizeof(p));
@@ -2122,20 +2155,8 @@ static void fill_pair_args(const FastArgs &f, PairArgs &p)
   p.kbm = h.kbm; p.nx = h.nx; p.klim_xm = h.klim_xm; p.klim_ym = h.klim_ym;
   p.lab_min = h.lab_min;
   p.defer_stride = f.defer_stride;
-  const double e6 = w.e6, slack = 1.0 + 4.76837158203125e-07;  // 1 + 2^-21
-  struct Axis { double W, e0; float *half, *ain, *aout, *e; };
-  Axis ax[2] = {{(double)w.Wf, (double)w.e0u, &p.half_w, &p.ain_u, &p.aout_u, &p.eu},
-                {(double)w.Hf, (double)w.e0v, &p.half_h, &p.ain_v, &p.aout_v, &p.ev}};
-  for (const Axis &a : ax) {
-    const double half = 0.5 * a.W;                      // exact in binary32 (W is an image size)
-    const double e = (e6 * (a.W + 1.0) + a.e0) * 1.001;  // >= E(q) for every |q| <= W + 1
-    *a.half = (float)half;
-    *a.e = std::nextafterf((float)e, INFINITY);
-    // |RN(q - W/2)| < ain  =>  E < q < W - E, hence every value within E(q) of q is in [0, W)
-    *a.ain = std::nextafterf((float)(half - (double)*a.e - a.W * 4.76837158203125e-07), 0.0f);
-    // |RN(q - W/2)| > aout  =>  q - E(q) >= W or q + E(q) < 0
-    *a.aout = std::nextafterf((float)(((a.W + a.e0) / (1.0 - e6) - half) * slack), INFINITY);
-  }
+  pair_axis_thresholds((double)w.Wf, (double)w.e6, (double)w.e0u, &p.half_w, &p.eu, &p.ain_u, &p.aout_u);
+  pair_axis_thresholds((double)w.Hf, (double)w.e6, (double)w.e0v, &p.half_h, &p.ev, &p.ain_v, &p.aout_v);
   p.inv_tile = 1.0f / (float)(1 << f.mask_shift);
   p.mask_tx = (unsigned)f.mask_tx;
   p.mask_stride = (unsigned)f.mask_stride;

@@ -136,6 +136,13 @@ GV_API int gv_graph_end(gv_ctx *ctx, int32_t *graph_id);
 GV_API int gv_graph_launch(gv_ctx *ctx, int32_t graph_id);
 GV_API int gv_graph_destroy(gv_ctx *ctx, int32_t graph_id);
 
+/* Host-only probe (needs no device): the thresholds of the certified image test of the fused point
+ * kernel for an image axis of `size` pixels with principal point c (ref intrinsics:
+ * src/object_detection.cpp:241-247): out[6] = {size/2, E, a_in, a_out, e6, e0} with
+ * |RN(q - size/2)| < a_in => certainly 0 <= u < size, > a_out => certainly outside, E the interval of
+ * the box tests.  For the CPU tests of the error analysis. */
+GV_API int gv_debug_pair_thresholds(double size, float c, float *out);
+
 /* ------------------------------------------------------------ fusion (R1-R5) --- */
 /* Camera rig.  K: ncam x 9 (ref: src/object_detection.cpp:241-247 setIntrinsicMatrix);
  * T_cam_lidar: ncam x 16, the float matrix pcl_ros::transformPointCloud applies

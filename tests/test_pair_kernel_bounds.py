@@ -16,6 +16,25 @@ f32, f64 = np.float32, np.float64
 U22 = 2.0 ** -22
 
 
+def host_pair_thresholds(W, c):
+    """The numbers the library itself uses (gv_debug_pair_thresholds: host-only, needs no GPU)."""
+    import ctypes as C
+    from grid_vision_b200 import _lib
+    out = np.zeros(6, f32)
+    rc = _lib.load().gv_debug_pair_thresholds(C.c_double(W), C.c_float(c), out.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    return out
+
+
+def test_python_thresholds_are_the_librarys():
+    """The emulation below restates fill_pair_args; this pins it to the real host code bit for bit."""
+    for W, c in ((416.0, 208.0), (640.0, 321.5), (1280.0, 600.25), (64.0, 10.0), (1920.0, 959.5)):
+        e6, e0, half, e, ain, aout = pair_thresholds(W, c)
+        got = host_pair_thresholds(W, c)
+        exp = np.array([half, e, ain, aout, e6, e0], f32)
+        assert np.array_equal(got.view(np.uint32), exp.view(np.uint32)), (W, c, got, exp)
+
+
 def pair_thresholds(W, c):
     """fill_pair_args for one axis (image size W, principal point c); all in double, rounded to the
     safe side exactly like the host code."""
